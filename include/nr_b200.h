@@ -1,0 +1,187 @@
+/*
+ * nr_b200.h -- C ABI of the B200-native rasterize / sample / approximate-gradient path.
+ *
+ * This is the drop-in boundary.  The reference binds its native code through a pybind11
+ * module (neural_renderer_torch/cuda/rasterize_cuda.cpp:93-99) whose live entry points are
+ * face_index_map_forward_safe (:55-65) and compute_weight_map_c (:81-90); everything around
+ * them is torch orchestration (neural_renderer_torch/rasterize.py:194-329) plus the
+ * Differentiation autograd function (neural_renderer_torch/differentiation.py:6-40).
+ * libnr_b200.so exports
+ *   (1) the same two operators with the same argument meaning (nr_face_index_map_forward_safe,
+ *       nr_compute_weight_map), and
+ *   (2) the fused forward / backward of the whole path that rasterize_core drives
+ *       (nr_rasterize_forward, nr_rasterize_backward, nr_differentiation_backward).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain pointers and
+ *     sizes only, no torch / ATen types;
+ *   - the caller owns every buffer (as in the reference, rasterize.py:32-33,71); kernels
+ *     write in place;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) of the CURRENT device
+ *     and the call returns without synchronising;
+ *   - return value: NR_OK or an error code; nr_last_error() gives the message of the
+ *     last failure on the calling thread.  CUDA launch errors are returned, not printf'd
+ *     (the reference only prints them, rasterize_cuda_kernel.cu:386-388).
+ *   - float tensors are float32, index tensors int32, layouts are C-contiguous.
+ */
+#ifndef NR_B200_H
+#define NR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NR_API __attribute__((visibility("default")))
+#else
+#define NR_API
+#endif
+
+enum {
+    NR_OK = 0,
+    NR_ERR_INVALID_ARGUMENT = 1,
+    NR_ERR_CUDA = 2,
+    NR_ERR_WORKSPACE_TOO_SMALL = 3
+};
+
+/* nrRasterConfig.flags */
+#define NR_DRAW_RGB 1         /* rasterize.py:244-249  */
+#define NR_DRAW_SILHOUETTES 2 /* rasterize.py:240-242  */
+#define NR_DRAW_DEPTH 4       /* rasterize.py:290-292  */
+#define NR_DRAW_BACKSIDE 8    /* rasterize_param.py:20 */
+#define NR_ANTI_ALIASING 16   /* rasterize.py:227-228, 321-328 */
+#define NR_DETERMINISTIC 32   /* backward: fixed-order reduction instead of float atomics */
+
+/* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */
+typedef struct nrRasterConfig {
+    int32_t batch;            /* B: views */
+    int32_t num_vertices;     /* nv */
+    int32_t num_faces;        /* nf */
+    int32_t image_size;       /* S: OUTPUT size; internal R = 2S with NR_ANTI_ALIASING */
+    int32_t flags;            /* NR_DRAW_* | NR_ANTI_ALIASING | ... */
+    float near_plane;         /* default 0.1   */
+    float far_plane;          /* default 100   */
+    float eps;                /* default 1e-5 (texture clamp, rasterize.py:121) */
+    float depth_min_delta;    /* 1e-4, the z-test hysteresis (rasterize.py:35) */
+    int32_t num_tex_vertices; /* nvt (0 when no texture) */
+    int32_t tex_height;       /* H */
+    int32_t tex_width;        /* W */
+} nrRasterConfig;
+
+/*
+ * Written by the forward into the workspace header and, when `stats_host` is given,
+ * copied asynchronously to that (pinned) host struct so the caller can check it after
+ * synchronising on its own event.  overflow != 0 means the (tile, face) pair list did
+ * not fit `pair_capacity`: the outputs of that call are undefined; call again with a
+ * workspace sized for at least `total_pairs`.
+ */
+typedef struct nrBinStats {
+    int32_t total_pairs;      /* sum over tiles of faces whose pixel bbox touches the tile */
+    int32_t max_tile_faces;   /* longest per-tile list */
+    int32_t overflow;         /* 1: pair list truncated, results invalid */
+    int32_t bad_index;        /* 1: a face referenced a vertex outside [0, nv) (face dropped) */
+} nrBinStats;
+
+NR_API int nr_abi_version(void);
+NR_API const char *nr_last_error(void);
+
+/* Number of channels the configuration renders: 3*rgb + silhouettes + depth. */
+NR_API int nr_num_channels(int32_t flags);
+
+/* Thin wrappers so a host without a CUDA binding (ctypes, cgo ...) can wait for the statistics. */
+NR_API int nr_event_create(void **event);
+NR_API int nr_event_destroy(void *event);
+NR_API int nr_event_synchronize(void *event);
+
+/* Bytes of scratch the forward needs for `pair_capacity` (tile, face) pairs. */
+NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity);
+
+/*
+ * Fused forward of rasterize_core (rasterize.py:194-329) without lights / backgrounds:
+ * face gather (:232), z-buffer (:235), weight map (:236), texture sampling (:249),
+ * silhouettes (:242), depth (:292), channel merge (:295-310), permute + flip (:315-316),
+ * 2x2 anti-aliasing mean (:321-328).
+ *
+ *   vertices            [B, nv, 3]   screen-space x, y in [-1, 1], z = depth
+ *   faces               [nf, 3]      vertex ids; NULL means face f uses vertices 3f, 3f+1, 3f+2
+ *                                    (i.e. `vertices` is the gathered [B, nf, 3, 3] tensor)
+ *   vertices_textures   [B, nvt, 2]  texel coordinates           (NR_DRAW_RGB only)
+ *   faces_textures      [nf, 3]      ids into vertices_textures  (NR_DRAW_RGB only)
+ *   textures            [B, 3, H, W]                             (NR_DRAW_RGB only)
+ *   face_index_map      [B, R, R]    out, -1 on background (never NULL)
+ *   weight_map          [B, R, R, 3] out, optional (NULL to skip)
+ *   depth_map           [B, R, R]    out, optional (NULL to skip); 1/sum(w/z), 0 on background
+ *   images              [B, C, S, S] out, channel order rgb, silhouette, depth
+ *   images_internal     [B, C, R, R] out, required with NR_ANTI_ALIASING (the backward
+ *                                    stencil runs at internal resolution), else may be NULL
+ *                                    (then `images` itself is the internal image)
+ *   workspace           nr_workspace_bytes(cfg, pair_capacity) bytes, 256-byte aligned
+ *   stats_host          optional pinned host nrBinStats
+ *   stats_event         optional cudaEvent_t (as void*, e.g. from nr_event_create) recorded right
+ *                       after the stats copy, i.e. BEFORE the raster kernel: waiting on it costs
+ *                       the binning kernels only
+ */
+NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
+                         const float *vertices_textures, const int32_t *faces_textures,
+                         const float *textures, int32_t *face_index_map, float *weight_map,
+                         float *depth_map, float *images, float *images_internal, void *workspace,
+                         size_t workspace_bytes, int64_t pair_capacity, nrBinStats *stats_host,
+                         void *stats_event, void *stream);
+
+/*
+ * Fused backward: AA / flip / permute backward, the Differentiation stencil
+ * (differentiation.py:13-36 with utils.py:75-101), coordinate_map -> faces -> vertices
+ * scatter (autograd of rasterize.py:91-97,232), sample_textures backward (:100-153) into
+ * textures, face z and vertices_textures, and depth-map backward (:80-88).
+ *
+ *   face_index_map      [B, R, R]    from the forward
+ *   images_internal     [B, C, R, R] from the forward (pass `images` when not anti-aliased)
+ *   grad_images         [B, C, S, S] upstream gradient
+ *   grad_vertices       [B, nv, 3]   out, ACCUMULATED into (caller zero-fills)
+ *   grad_textures       [B, 3, H, W] out, accumulated, optional
+ *   grad_vertices_textures [B, nvt, 2] out, accumulated, optional
+ */
+NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
+                          const float *vertices_textures, const int32_t *faces_textures,
+                          const float *textures, const int32_t *face_index_map,
+                          const float *images_internal, const float *grad_images,
+                          float *grad_vertices, float *grad_textures,
+                          float *grad_vertices_textures, void *stream);
+
+/*
+ * Differentiation.backward (differentiation.py:13-36) on channels-last tensors, as the
+ * public differentiation(images, coordinates) op sees them:
+ *   images, grad_output [B, R, R, C] -> grad_coordinates [B, R, R, 2] (x, y), overwritten.
+ */
+NR_API int nr_differentiation_backward(const float *images, const float *grad_output,
+                                float *grad_coordinates, int32_t batch, int32_t image_size,
+                                int32_t channels, void *stream);
+
+/*
+ * Same operator as face_index_map_forward_safe (rasterize_cuda.cpp:55-65):
+ *   faces [B, nf, 3, 3], face_index [B*S*S] written in place (pre-fill not required).
+ * `eps` is accepted and unused, like in the reference kernel.  Scratch is taken from a
+ * per-device cache owned by the library (this call synchronises once on the bin statistics).
+ */
+NR_API int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int32_t batch,
+                                   int32_t num_faces, int32_t image_size, float near_plane,
+                                   float far_plane, int32_t draw_backside, float eps,
+                                   float depth_min_delta, void *stream);
+
+/*
+ * Same operator as compute_weight_map_c (rasterize_cuda.cpp:81-90):
+ *   faces [B, nf, 3, 3], face_index_map [B*S*S], weight_map [B*S*S, 3]; only foreground
+ *   pixels are written (the caller zero-fills, rasterize.py:71).
+ */
+NR_API int nr_compute_weight_map(const float *faces, const int32_t *face_index_map, float *weight_map,
+                          int32_t batch, int32_t num_faces, int32_t image_size, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NR_B200_H */

@@ -1,0 +1,331 @@
+// nr_abi.cu -- extern "C" entry points declared in include/nr_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/nr_b200.h"
+#include "nr_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return NR_ERR_CUDA;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carve {
+    nr::BinHeader *hdr;
+    int *tile_count, *tile_offset, *tile_cursor;
+    nr::FaceRec *rec;
+    int32_t *pairs;
+    size_t bytes;
+};
+
+// header and tile_count must be adjacent (one memset clears both)
+Carve carve(void *base, int B, int nf, int R, long long pair_capacity) {
+    const int ntx = (R + nr::TILE - 1) / nr::TILE;
+    const size_t nt = (size_t)B * ntx * ntx;
+    char *p = (char *)base;
+    size_t off = 0;
+    Carve c;
+    c.hdr = (nr::BinHeader *)(p + off);
+    off += sizeof(nr::BinHeader);
+    c.tile_count = (int *)(p + off);
+    off = align256(off + nt * sizeof(int));
+    c.tile_offset = (int *)(p + off);
+    off = align256(off + nt * sizeof(int));
+    c.tile_cursor = (int *)(p + off);
+    off = align256(off + nt * sizeof(int));
+    c.rec = (nr::FaceRec *)(p + off);
+    off = align256(off + (size_t)B * nf * sizeof(nr::FaceRec));
+    c.pairs = (int32_t *)(p + off);
+    off = align256(off + (size_t)(pair_capacity > 0 ? pair_capacity : 1) * sizeof(int32_t));
+    c.bytes = off;
+    return c;
+}
+
+int sm_count_cached() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+int check_config(const nrRasterConfig *cfg) {
+    if (!cfg) return fail(NR_ERR_INVALID_ARGUMENT, "config is NULL");
+    if (cfg->batch < 0 || cfg->num_vertices < 0 || cfg->num_faces < 0 || cfg->image_size <= 0)
+        return fail(NR_ERR_INVALID_ARGUMENT, "negative extent or image_size <= 0");
+    if (cfg->batch > 65535) return fail(NR_ERR_INVALID_ARGUMENT, "batch > 65535");
+    const long long R = (long long)cfg->image_size * ((cfg->flags & NR_ANTI_ALIASING) ? 2 : 1);
+    if (R > 32768) return fail(NR_ERR_INVALID_ARGUMENT, "internal resolution > 32768");
+    if (!(cfg->flags & (NR_DRAW_RGB | NR_DRAW_SILHOUETTES | NR_DRAW_DEPTH)))
+        return fail(NR_ERR_INVALID_ARGUMENT, "nothing to draw: no NR_DRAW_* flag");
+    return NR_OK;
+}
+
+// per-device scratch for the two reference-signature operators
+struct CompatScratch {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    long long pair_capacity = 0;
+    nrBinStats *stats_host = nullptr;
+};
+std::mutex g_compat_mu;
+CompatScratch g_compat[64];
+
+}  // namespace
+
+extern "C" {
+
+int nr_abi_version(void) { return NR_ABI_VERSION; }
+const char *nr_last_error(void) { return g_err; }
+
+int nr_num_channels(int32_t flags) {
+    return ((flags & NR_DRAW_RGB) ? 3 : 0) + ((flags & NR_DRAW_SILHOUETTES) ? 1 : 0) +
+           ((flags & NR_DRAW_DEPTH) ? 1 : 0);
+}
+
+int nr_event_create(void **event) {
+    if (!event) return fail(NR_ERR_INVALID_ARGUMENT, "event is NULL");
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaEventCreate");
+    *event = (void *)ev;
+    return NR_OK;
+}
+int nr_event_destroy(void *event) {
+    if (!event) return NR_OK;
+    cudaError_t e = cudaEventDestroy((cudaEvent_t)event);
+    return e == cudaSuccess ? NR_OK : fail_cuda(e, "cudaEventDestroy");
+}
+int nr_event_synchronize(void *event) {
+    if (!event) return fail(NR_ERR_INVALID_ARGUMENT, "event is NULL");
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);
+    return e == cudaSuccess ? NR_OK : fail_cuda(e, "cudaEventSynchronize");
+}
+
+size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
+    if (!cfg) return 0;
+    const int R = cfg->image_size * ((cfg->flags & NR_ANTI_ALIASING) ? 2 : 1);
+    return carve(nullptr, cfg->batch, cfg->num_faces, R, pair_capacity).bytes;
+}
+
+int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
+                         const float *vertices_textures, const int32_t *faces_textures,
+                         const float *textures, int32_t *face_index_map, float *weight_map,
+                         float *depth_map, float *images, float *images_internal, void *workspace,
+                         size_t workspace_bytes, int64_t pair_capacity, nrBinStats *stats_host,
+                         void *stats_event, void *stream_) {
+    if (int rc = check_config(cfg)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
+    const int R = cfg->image_size * (aa ? 2 : 1);
+    if (!vertices && cfg->batch * cfg->num_faces > 0) return fail(NR_ERR_INVALID_ARGUMENT, "vertices is NULL");
+    if (!face_index_map) return fail(NR_ERR_INVALID_ARGUMENT, "face_index_map is NULL");
+    if (rgb && (!vertices_textures || !faces_textures || !textures))
+        return fail(NR_ERR_INVALID_ARGUMENT, "NR_DRAW_RGB needs vertices_textures, faces_textures and textures");
+    if (rgb && (cfg->tex_height <= 0 || cfg->tex_width <= 0 || cfg->num_tex_vertices <= 0))
+        return fail(NR_ERR_INVALID_ARGUMENT, "NR_DRAW_RGB needs positive texture extents");
+    if (images && aa && !images_internal)
+        return fail(NR_ERR_INVALID_ARGUMENT, "anti-aliasing needs images_internal");
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(NR_ERR_INVALID_ARGUMENT, "workspace NULL or not 256-byte aligned");
+    if (pair_capacity < 0 || pair_capacity > 0x7fffffffLL) return fail(NR_ERR_INVALID_ARGUMENT, "pair_capacity out of range");
+    const Carve c = carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity);
+    if (c.bytes > workspace_bytes) return fail(NR_ERR_WORKSPACE_TOO_SMALL, "workspace smaller than nr_workspace_bytes()");
+    if (cfg->batch == 0) return NR_OK;
+
+    nr::BinningArgs ba;
+    ba.verts = vertices;
+    ba.faces = faces;
+    ba.B = cfg->batch;
+    ba.nv = cfg->num_vertices;
+    ba.nf = cfg->num_faces;
+    ba.R = R;
+    ba.draw_backside = (cfg->flags & NR_DRAW_BACKSIDE) ? 1 : 0;
+    ba.ntx = (R + nr::TILE - 1) / nr::TILE;
+    ba.rec = c.rec;
+    ba.tile_count = c.tile_count;
+    ba.tile_offset = c.tile_offset;
+    ba.tile_cursor = c.tile_cursor;
+    ba.pairs = c.pairs;
+    ba.pair_capacity = pair_capacity;
+    ba.hdr = c.hdr;
+    ba.sm_count = sm_count_cached();
+    cudaError_t e = nr::launch_binning(ba, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "binning");
+    if (stats_host) {
+        e = cudaMemcpyAsync(stats_host, c.hdr, sizeof(nrBinStats), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "stats copy");
+    }
+    if (stats_event) {
+        e = cudaEventRecord((cudaEvent_t)stats_event, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "stats event");
+    }
+
+    nr::RasterArgs ra;
+    ra.rec = c.rec;
+    ra.tile_count = c.tile_count;
+    ra.tile_offset = c.tile_offset;
+    ra.pairs = c.pairs;
+    ra.hdr = c.hdr;
+    ra.B = cfg->batch;
+    ra.nf = cfg->num_faces;
+    ra.R = R;
+    ra.S = cfg->image_size;
+    ra.ntx = ba.ntx;
+    ra.C = nr_num_channels(cfg->flags);
+    ra.flags = cfg->flags;
+    ra.near_plane = cfg->near_plane;
+    ra.far_plane = cfg->far_plane;
+    ra.eps = cfg->eps;
+    ra.delta = cfg->depth_min_delta;
+    ra.vt = vertices_textures;
+    ra.ft = faces_textures;
+    ra.tex = textures;
+    ra.nvt = cfg->num_tex_vertices;
+    ra.H = cfg->tex_height;
+    ra.W = cfg->tex_width;
+    ra.fim = face_index_map;
+    ra.wmap = weight_map;
+    ra.dmap = depth_map;
+    ra.images = images;
+    ra.internal = images_internal;
+    e = nr::launch_raster(ra, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "raster");
+    return NR_OK;
+}
+
+int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
+                          const float *vertices_textures, const int32_t *faces_textures,
+                          const float *textures, const int32_t *face_index_map,
+                          const float *images_internal, const float *grad_images,
+                          float *grad_vertices, float *grad_textures,
+                          float *grad_vertices_textures, void *stream_) {
+    if (int rc = check_config(cfg)) return rc;
+    const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
+    if (!vertices || !face_index_map || !images_internal || !grad_images || !grad_vertices)
+        return fail(NR_ERR_INVALID_ARGUMENT, "backward: a required pointer is NULL");
+    if (rgb && (!vertices_textures || !faces_textures || !textures))
+        return fail(NR_ERR_INVALID_ARGUMENT, "NR_DRAW_RGB needs vertices_textures, faces_textures and textures");
+    if (cfg->batch == 0) return NR_OK;
+    nr::BackwardArgs a;
+    a.verts = vertices;
+    a.faces = faces;
+    a.vt = vertices_textures;
+    a.ft = faces_textures;
+    a.tex = textures;
+    a.fim = face_index_map;
+    a.internal = images_internal;
+    a.grad_images = grad_images;
+    a.grad_verts = grad_vertices;
+    a.grad_tex = grad_textures;
+    a.grad_vt = grad_vertices_textures;
+    a.B = cfg->batch;
+    a.nv = cfg->num_vertices;
+    a.nf = cfg->num_faces;
+    a.S = cfg->image_size;
+    a.R = cfg->image_size * (aa ? 2 : 1);
+    a.ntx = (a.R + nr::TILE - 1) / nr::TILE;
+    a.C = nr_num_channels(cfg->flags);
+    a.flags = cfg->flags;
+    a.nvt = cfg->num_tex_vertices;
+    a.H = cfg->tex_height;
+    a.W = cfg->tex_width;
+    a.eps = cfg->eps;
+    cudaError_t e = nr::launch_backward(a, (cudaStream_t)stream_);
+    if (e != cudaSuccess) return fail_cuda(e, "backward");
+    return NR_OK;
+}
+
+int nr_differentiation_backward(const float *images, const float *grad_output,
+                                float *grad_coordinates, int32_t batch, int32_t image_size,
+                                int32_t channels, void *stream_) {
+    if (!images || !grad_output || !grad_coordinates)
+        return fail(NR_ERR_INVALID_ARGUMENT, "differentiation: NULL pointer");
+    if (batch < 0 || image_size <= 0 || channels <= 0)
+        return fail(NR_ERR_INVALID_ARGUMENT, "differentiation: bad extents");
+    cudaError_t e = nr::launch_differentiation_backward(images, grad_output, grad_coordinates, batch,
+                                                        image_size, channels, (cudaStream_t)stream_);
+    if (e != cudaSuccess) return fail_cuda(e, "differentiation backward");
+    return NR_OK;
+}
+
+int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int32_t batch,
+                                   int32_t num_faces, int32_t image_size, float near_plane,
+                                   float far_plane, int32_t draw_backside, float eps,
+                                   float depth_min_delta, void *stream_) {
+    (void)eps;   // unused by the reference kernel as well (rasterize_cuda_kernel.cu:61)
+    if (!faces || !face_index) return fail(NR_ERR_INVALID_ARGUMENT, "faces / face_index is NULL");
+    nrRasterConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.batch = batch;
+    cfg.num_vertices = num_faces * 3;
+    cfg.num_faces = num_faces;
+    cfg.image_size = image_size;
+    cfg.flags = NR_DRAW_SILHOUETTES | (draw_backside ? NR_DRAW_BACKSIDE : 0);
+    cfg.near_plane = near_plane;
+    cfg.far_plane = far_plane;
+    cfg.eps = 1e-5f;
+    cfg.depth_min_delta = depth_min_delta;
+    if (int rc = check_config(&cfg)) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return fail(NR_ERR_INVALID_ARGUMENT, "device ordinal >= 64");
+    std::lock_guard<std::mutex> lock(g_compat_mu);
+    CompatScratch &s = g_compat[dev];
+    if (!s.stats_host) {
+        cudaError_t e = cudaMallocHost((void **)&s.stats_host, sizeof(nrBinStats));
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMallocHost");
+    }
+    long long cap = s.pair_capacity > 0 ? s.pair_capacity : (long long)batch * num_faces * 4 + 1024;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const size_t need = nr_workspace_bytes(&cfg, cap);
+        if (need > s.bytes) {
+            cudaStreamSynchronize(stream);
+            if (s.ptr) cudaFree(s.ptr);
+            s.ptr = nullptr;
+            s.bytes = 0;
+            cudaError_t e = cudaMalloc(&s.ptr, need);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)");
+            s.bytes = need;
+        }
+        s.pair_capacity = cap;
+        int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
+                                      nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, stream);
+        if (rc != NR_OK) return rc;
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");
+        if (!s.stats_host->overflow) return NR_OK;
+        cap = (long long)s.stats_host->total_pairs + 1024;
+    }
+    return fail(NR_ERR_WORKSPACE_TOO_SMALL, "pair list still overflowing after regrowth");
+}
+
+int nr_compute_weight_map(const float *faces, const int32_t *face_index_map, float *weight_map,
+                          int32_t batch, int32_t num_faces, int32_t image_size, void *stream_) {
+    if (!faces || !face_index_map || !weight_map) return fail(NR_ERR_INVALID_ARGUMENT, "NULL pointer");
+    if (batch < 0 || num_faces < 0 || image_size <= 0) return fail(NR_ERR_INVALID_ARGUMENT, "bad extents");
+    cudaError_t e = nr::launch_weight_map_compat(faces, face_index_map, weight_map, batch, num_faces,
+                                                 image_size, (cudaStream_t)stream_);
+    if (e != cudaSuccess) return fail_cuda(e, "compute_weight_map");
+    return NR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// nr_binning.cu -- per-face setup and tile binning.
+//
+// Replaces the O(B * S^2 * nf) "every pixel scans every face" loop of the reference
+// (rasterize_cuda_kernel.cu:82) by per-tile face lists.  The reference z-test is a
+// SEQUENTIAL scan with a 1e-4 hysteresis (:145-148), so its result depends on the order
+// faces are visited; every tile list is therefore delivered in ascending face index.
+//
+//   k_setup_count : one thread per (view, face). Gathers the 3 vertices (rasterize.py:232),
+//                   applies the tests that do not depend on the pixel (back-face :100-104,
+//                   degenerate :118-121), computes the EXACT set of pixel columns / rows whose
+//                   centre passes the bounding-box test (:94-97), writes a 48-byte record and
+//                   counts the face into every 16x16 tile its pixel box touches.
+//   k_scan_tiles  : exclusive prefix sum of the per-tile counts (one CTA per view).
+//   k_scatter     : writes face ids into the tile segments (slot order is arbitrary ...)
+//   k_sort_long   : ... so segments are sorted: long ones here in global memory, short ones
+//                   in shared memory by the raster kernel itself.
+#include "nr_kernels.h"
+
+namespace nr {
+
+__global__ void __launch_bounds__(256)
+k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces, int B, int nv,
+              int nf, int R, int draw_backside, FaceRec *__restrict__ rec,
+              int *__restrict__ tile_count, int ntx, BinHeader *__restrict__ hdr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * nf) return;
+    const int b = (int)(idx / nf), f = (int)(idx % nf);
+
+    int i0, i1, i2;
+    if (faces) {
+        i0 = faces[3 * f + 0];
+        i1 = faces[3 * f + 1];
+        i2 = faces[3 * f + 2];
+    } else {
+        i0 = 3 * f;
+        i1 = i0 + 1;
+        i2 = i0 + 2;
+    }
+    FaceRec r;
+    r.q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.q1 = r.q0;
+    r.q2 = make_float4(0.f, __uint_as_float(DEAD_BBOX), 0.f, 0.f);
+    if ((unsigned)i0 >= (unsigned)nv || (unsigned)i1 >= (unsigned)nv || (unsigned)i2 >= (unsigned)nv) {
+        hdr->bad_index = 1;
+        rec[idx] = r;
+        return;
+    }
+    const float *vb = verts + (size_t)b * nv * 3;
+    const float x0 = vb[3 * i0], y0 = vb[3 * i0 + 1], z0 = vb[3 * i0 + 2];
+    const float x1 = vb[3 * i1], y1 = vb[3 * i1 + 1], z1 = vb[3 * i1 + 2];
+    const float x2 = vb[3 * i2], y2 = vb[3 * i2 + 1], z2 = vb[3 * i2 + 2];
+    r.q0 = make_float4(x0, y0, z0, x1);
+    r.q1 = make_float4(y1, z1, x2, y2);
+    r.q2.x = z2;
+
+    // A face with a non-finite x or y can never win a pixel in the reference: its barycentric
+    // weights divide inf by inf (NaN depth), and NaN fails the z-test (DESIGN.md "Dropped faces").
+    bool alive = isfinite(x0) && isfinite(x1) && isfinite(x2) && isfinite(y0) && isfinite(y1) &&
+                 isfinite(y2);
+    // rasterize_cuda_kernel.cu:100-104, two rounded products
+    if (alive && !draw_backside) {
+        const float a = __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(x1, x0));
+        const float c = __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x2, x0));
+        if (a > c) alive = false;
+    }
+    // :118-121
+    if (alive) {
+        const float det = __fmaf_rn(x1, __fsub_rn(y2, y0),
+                                    __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
+        if ((double)fabsf(det) < 0.00000001) alive = false;
+    }
+    int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+    if (alive) {
+        // :94-97  pixel passes iff  min <= centre <= max  on both axes
+        xlo = first_pixel_ge(fminf(x0, fminf(x1, x2)), R);
+        xhi = last_pixel_le(fmaxf(x0, fmaxf(x1, x2)), R);
+        ylo = first_pixel_ge(fminf(y0, fminf(y1, y2)), R);
+        yhi = last_pixel_le(fmaxf(y0, fmaxf(y1, y2)), R);
+        if (xlo > xhi || ylo > yhi) alive = false;
+    }
+    if (alive) {
+        r.q2.y = __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16));
+        r.q2.z = __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16));
+    }
+    rec[idx] = r;
+    if (!alive) return;
+
+    int *tc = tile_count + (size_t)b * ntx * ntx;
+    const int tx0 = xlo / TILE, tx1 = xhi / TILE, ty0 = ylo / TILE, ty1 = yhi / TILE;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * ntx + tx], 1);
+}
+
+// One CTA per view: exclusive scan of its tile counts; the view's base offset in the global
+// pair list is claimed with one atomicAdd (segment placement is arbitrary, content is not).
+__global__ void __launch_bounds__(1024)
+k_scan_tiles(const int *__restrict__ tile_count, int *__restrict__ tile_offset,
+             int *__restrict__ tile_cursor, int nt, long long pair_capacity,
+             BinHeader *__restrict__ hdr) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int *tc = tile_count + (size_t)b * nt;
+
+    // pass 1: view total and longest list
+    int sum = 0, mx = 0;
+    for (int i = tid; i < nt; i += blockDim.x) {
+        const int c = tc[i];
+        sum += c;
+        mx = max(mx, c);
+    }
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) s_warp[wid] = sum;
+    if (lane == 0 && mx > 0) atomicMax(&hdr->max_tile_faces, mx);
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_warp[w];
+        const int base = atomicAdd(&hdr->total_pairs, tot);
+        if ((long long)base + tot > pair_capacity) hdr->overflow = 1;
+        s_base = base;
+    }
+    __syncthreads();
+    int carry = s_base;
+    __syncthreads();
+
+    // pass 2: chunked block scan
+    for (int c0 = 0; c0 < nt; c0 += blockDim.x) {
+        const int i = c0 + tid;
+        const int v = (i < nt) ? tc[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const int warp_excl = (wid == 0) ? 0 : s_warp[wid - 1];
+        const int excl = carry + warp_excl + inc - v;
+        if (i < nt) {
+            tile_offset[(size_t)b * nt + i] = excl;
+            tile_cursor[(size_t)b * nt + i] = excl;
+        }
+        carry += s_warp[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restrict__ tile_cursor,
+          int32_t *__restrict__ pairs, long long pair_capacity, const BinHeader *__restrict__ hdr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * nf) return;
+    if (hdr->overflow) return;
+    const float4 q2 = reinterpret_cast<const float4 *>(rec + idx)[2];
+    const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+    const int xlo = bx & 0xffff, xhi = bx >> 16;
+    if (xlo > xhi) return;
+    const int ylo = by & 0xffff, yhi = by >> 16;
+    const int b = (int)(idx / nf), f = (int)(idx % nf);
+    int *cur = tile_cursor + (size_t)b * ntx * ntx;
+    const int tx0 = xlo / TILE, tx1 = xhi / TILE, ty0 = ylo / TILE, ty1 = yhi / TILE;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int slot = atomicAdd(&cur[ty * ntx + tx], 1);
+            if (slot < pair_capacity) pairs[slot] = f;
+        }
+}
+
+// Ascending in-place sort of the segments that are too long for the raster kernel's
+// shared-memory sort.  Same-direction bitonic network over a virtual power-of-two length
+// (indices >= n behave as +inf and never move), one CTA per long segment, grid-stride over tiles.
+__global__ void __launch_bounds__(256)
+k_sort_long(const int *__restrict__ tile_count, const int *__restrict__ tile_offset, int total_tiles,
+            int32_t *__restrict__ pairs, int threshold, const BinHeader *__restrict__ hdr) {
+    if (hdr->overflow || hdr->max_tile_faces <= threshold) return;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n = tile_count[t];
+        if (n <= threshold) continue;
+        int32_t *a = pairs + tile_offset[t];
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        for (int k = 2; k <= np2; k <<= 1) {
+            // first stage of the merge: compare i with its mirror inside the k-block
+            for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                const int blk = i / (k / 2), off = i % (k / 2);
+                const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+                if (hi < n) {
+                    const int x = a[lo], y = a[hi];
+                    if (x > y) {
+                        a[lo] = y;
+                        a[hi] = x;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = k / 4; j >= 1; j >>= 1) {
+                for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                    const int lo = (i / j) * 2 * j + (i % j), hi = lo + j;
+                    if (hi < n) {
+                        const int x = a[lo], y = a[hi];
+                        if (x > y) {
+                            a[lo] = y;
+                            a[hi] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
+    const int nt = a.ntx * a.ntx;
+    // header + tile counts are contiguous in the workspace: one memset
+    cudaError_t e = cudaMemsetAsync(a.hdr, 0, sizeof(BinHeader) + sizeof(int) * (size_t)a.B * nt, stream);
+    if (e != cudaSuccess) return e;
+    const long long nface = (long long)a.B * a.nf;
+    if (nface > 0) {
+        const unsigned blocks = (unsigned)((nface + 255) / 256);
+        k_setup_count<<<blocks, 256, 0, stream>>>(a.verts, a.faces, a.B, a.nv, a.nf, a.R,
+                                                  a.draw_backside, a.rec, a.tile_count, a.ntx, a.hdr);
+    }
+    k_scan_tiles<<<a.B, 1024, 0, stream>>>(a.tile_count, a.tile_offset, a.tile_cursor, nt,
+                                           a.pair_capacity, a.hdr);
+    if (nface > 0) {
+        const unsigned blocks = (unsigned)((nface + 255) / 256);
+        k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_cursor, a.pairs,
+                                              a.pair_capacity, a.hdr);
+        k_sort_long<<<a.sm_count * 2, 256, 0, stream>>>(a.tile_count, a.tile_offset, a.B * nt, a.pairs,
+                                                        SMEM_SORT_CAP, a.hdr);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace nr

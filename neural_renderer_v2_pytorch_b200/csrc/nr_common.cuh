@@ -1,0 +1,144 @@
+// nr_common.cuh -- shared device code of the B200-native rasterizer.
+//
+// The z-buffer result must be bit-identical to the reference kernel
+// (neural_renderer_torch/cuda/rasterize_cuda_kernel.cu:52-153), whose SASS contracts some
+// products into FMAs and not others.  Everything that decides coverage or depth is therefore
+// spelled with explicit rounding intrinsics (never re-contracted by nvcc); the formulas are the
+// ones in oracle/nr_oracle.c, which cites the reference line by line.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nr {
+
+constexpr int TILE = 16;            // tile edge in pixels (internal resolution)
+constexpr int TILE_THREADS = 256;   // one thread per pixel of a tile
+constexpr int WARP_BW = 8;          // a warp owns an 8 x 4 pixel block of the tile
+constexpr int WARP_BH = 4;
+
+// nrRasterConfig.flags (include/nr_b200.h)
+constexpr int FLAG_RGB = 1, FLAG_SIL = 2, FLAG_DEPTH = 4, FLAG_BACKSIDE = 8, FLAG_AA = 16,
+              FLAG_DETERMINISTIC = 32;
+
+// Workspace header (device side). Layout shared by all kernels.
+struct BinHeader {
+    int total_pairs;
+    int max_tile_faces;
+    int overflow;
+    int bad_index;
+    int pad[60];
+};
+static_assert(sizeof(BinHeader) == 256, "header is one 256-byte block");
+
+// Per (view, face) record written by the setup kernel: 48 bytes, three float4 loads.
+//   q0 = x0 y0 z0 x1 | q1 = y1 z1 x2 y2 | q2 = z2, bbox_x (lo | hi << 16), bbox_y, unused
+// A dead face (culled, degenerate, non-finite or off-screen) has bbox_x = 0x0000ffff (lo > hi).
+struct FaceRec {
+    float4 q0, q1, q2;
+};
+constexpr uint32_t DEAD_BBOX = 0x0000ffffu;
+
+__device__ __forceinline__ float pix_center(int i, int R) {
+    // rasterize_cuda_kernel.cu:76-77: (2.*i + 1 - is) / is evaluated in double then narrowed;
+    // numerator and denominator are exact small integers so this is one IEEE float division.
+    return __fdiv_rn((float)(2 * i + 1 - R), (float)R);
+}
+
+// smallest i in [0, R] with pix_center(i) >= v   (R if none)
+__device__ __forceinline__ int first_pixel_ge(float v, int R) {
+    const double t = ((double)v * R + (double)(R - 1)) * 0.5;
+    int i;
+    if (!(t > 0.0)) i = 0;
+    else if (t >= (double)R) i = R;
+    else i = (int)ceil(t);
+    while (i > 0 && pix_center(i - 1, R) >= v) --i;
+    while (i < R && pix_center(i, R) < v) ++i;
+    return i;
+}
+
+// largest i in [-1, R-1] with pix_center(i) <= v   (-1 if none)
+__device__ __forceinline__ int last_pixel_le(float v, int R) {
+    const double t = ((double)v * R + (double)(R - 1)) * 0.5;
+    int i;
+    if (!(t >= 0.0)) i = -1;
+    else if (t >= (double)(R - 1)) i = R - 1;
+    else i = (int)floor(t);
+    while (i < R - 1 && pix_center(i + 1, R) <= v) ++i;
+    while (i >= 0 && pix_center(i, R) > v) --i;
+    return i;
+}
+
+// Raw (un-normalised) barycentric numerators, rasterize_cuda_kernel.cu:130-132 / :276-278.
+__device__ __forceinline__ void raw_weights(float xp, float yp, float x0, float y0, float x1,
+                                            float y1, float x2, float y2, float &w0, float &w1,
+                                            float &w2) {
+    w0 = __fadd_rn(__fmaf_rn(yp, __fsub_rn(x2, x1), __fmul_rn(xp, __fsub_rn(y1, y2))),
+                   __fmaf_rn(x1, y2, -__fmul_rn(x2, y1)));
+    w1 = __fadd_rn(__fmaf_rn(yp, __fsub_rn(x0, x2), __fmul_rn(xp, __fsub_rn(y2, y0))),
+                   __fmaf_rn(x2, y0, -__fmul_rn(x0, y2)));
+    w2 = __fadd_rn(__fmaf_rn(yp, __fsub_rn(x1, x0), __fmul_rn(xp, __fsub_rn(y0, y1))),
+                   __fmaf_rn(x0, y1, -__fmul_rn(x1, y0)));
+}
+
+// compute_weight_map_cuda_kernel, rasterize_cuda_kernel.cu:279-306, from the raw numerators.
+__device__ __forceinline__ void normalize_weights(float &w0, float &w1, float &w2) {
+    if (__fadd_rn(__fadd_rn(w0, w1), w2) < 0.f) {
+        w0 = -w0;
+        w1 = -w1;
+        w2 = -w2;
+    }
+    w0 = fmaxf(w0, 0.f);
+    w1 = fmaxf(w1, 0.f);
+    w2 = fmaxf(w2, 0.f);
+    const float s = __fadd_rn(__fadd_rn(w0, w1), w2);
+    w0 = fmaxf(fminf(__fdiv_rn(w0, s), 1.f), 0.f);
+    w1 = fmaxf(fminf(__fdiv_rn(w1, s), 1.f), 0.f);
+    w2 = fmaxf(fminf(__fdiv_rn(w2, s), 1.f), 0.f);
+}
+
+// utils.maximum (utils.py:91-101) on scalars.
+__device__ __forceinline__ float nr_maximum(float r, float l) {
+    if (fmaxf(r, l) <= 0.f) return 0.f;
+    if (fabsf(__fsub_rn(r, l)) < 1e-4f) return 0.f;
+    return (r > l) ? -r : l;
+}
+
+// Perspective-correct texel coordinate of a foreground pixel, rasterize.py:111-121, with every
+// operation rounded separately like the chain of torch ops it restates.  Forward and backward both
+// call this, so they agree on which four texels a pixel touches.
+struct TexCoord {
+    float depth, nx, ny;   // 1 / sum(w/z'), sum(w u / z'), sum(w v / z')
+    float x0, y0;          // before the clamp
+    float xf, yf;          // after the clamp to [min corner, max corner - eps]
+    float zz[3];           // z + 1e-10
+};
+__device__ __forceinline__ TexCoord texel_coord(const float q[3], const float z[3], const float u[3],
+                                                const float v[3], float eps) {
+    TexCoord t;
+    t.zz[0] = __fadd_rn(z[0], 1e-10f);
+    t.zz[1] = __fadd_rn(z[1], 1e-10f);
+    t.zz[2] = __fadd_rn(z[2], 1e-10f);
+    const float a0 = __fadd_rn(__fdiv_rn(q[0], t.zz[0]), 1e-10f);
+    const float a1 = __fadd_rn(__fdiv_rn(q[1], t.zz[1]), 1e-10f);
+    const float a2 = __fadd_rn(__fdiv_rn(q[2], t.zz[2]), 1e-10f);
+    t.depth = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(a0, a1), a2));
+    t.nx = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(q[0], u[0]), t.zz[0]), __fdiv_rn(__fmul_rn(q[1], u[1]), t.zz[1])),
+                     __fdiv_rn(__fmul_rn(q[2], u[2]), t.zz[2]));
+    t.ny = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(q[0], v[0]), t.zz[0]), __fdiv_rn(__fmul_rn(q[1], v[1]), t.zz[1])),
+                     __fdiv_rn(__fmul_rn(q[2], v[2]), t.zz[2]));
+    t.x0 = __fmul_rn(t.nx, t.depth);
+    t.y0 = __fmul_rn(t.ny, t.depth);
+    t.xf = fminf(fmaxf(t.x0, fminf(u[0], fminf(u[1], u[2]))), __fsub_rn(fmaxf(u[0], fmaxf(u[1], u[2])), eps));
+    t.yf = fminf(fmaxf(t.y0, fminf(v[0], fminf(v[1], v[2]))), __fsub_rn(fmaxf(v[0], fmaxf(v[1], v[2])), eps));
+    return t;
+}
+
+// Thread -> pixel mapping inside a tile: warp w owns the 8x4 block at
+// ((w & 1) * 8, (w >> 1) * 4); lane l is pixel (l & 7, l >> 3) of the block.
+__device__ __forceinline__ void tile_pixel(int tid, int &px, int &py) {
+    const int w = tid >> 5, l = tid & 31;
+    px = (w & 1) * WARP_BW + (l & 7);
+    py = (w >> 1) * WARP_BH + (l >> 3);
+}
+
+}  // namespace nr

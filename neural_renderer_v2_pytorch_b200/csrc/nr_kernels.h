@@ -1,0 +1,65 @@
+// nr_kernels.h -- internal launcher interfaces (not part of the C ABI).
+#pragma once
+#include "nr_common.cuh"
+
+namespace nr {
+
+// Tile lists up to this many faces are sorted in shared memory by the raster kernel;
+// longer ones by k_sort_long in global memory.
+constexpr int SMEM_SORT_CAP = 1024;
+
+struct BinningArgs {
+    const float *verts;
+    const int32_t *faces;   // may be null: face f = vertices 3f..3f+2
+    int B, nv, nf, R, draw_backside, ntx;
+    FaceRec *rec;
+    int *tile_count, *tile_offset, *tile_cursor;
+    int32_t *pairs;
+    long long pair_capacity;
+    BinHeader *hdr;
+    int sm_count;
+};
+cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
+
+struct RasterArgs {
+    const FaceRec *rec;
+    const int *tile_count, *tile_offset;
+    const int32_t *pairs;
+    const BinHeader *hdr;
+    int B, nf, R, S, ntx, C, flags;
+    float near_plane, far_plane, eps, delta;
+    const float *vt;        // [B, nvt, 2]
+    const int32_t *ft;      // [nf, 3]
+    const float *tex;       // [B, 3, H, W]
+    int nvt, H, W;
+    int32_t *fim;           // [B, R, R]
+    float *wmap;            // [B, R, R, 3] or null
+    float *dmap;            // [B, R, R] or null
+    float *images;          // [B, C, S, S] or null (compat call renders no image)
+    float *internal;        // [B, C, R, R] (AA) or null
+};
+cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);
+
+struct BackwardArgs {
+    const float *verts;     // [B, nv, 3]
+    const int32_t *faces;   // [nf, 3] or null
+    const float *vt;
+    const int32_t *ft;
+    const float *tex;
+    const int32_t *fim;
+    const float *internal;  // [B, C, R, R] flipped planar
+    const float *grad_images;   // [B, C, S, S]
+    float *grad_verts, *grad_tex, *grad_vt;
+    int B, nv, nf, R, S, ntx, C, flags, nvt, H, W;
+    float eps;
+};
+cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream);
+
+cudaError_t launch_differentiation_backward(const float *images, const float *grad_output,
+                                            float *grad_coordinates, int B, int R, int C,
+                                            cudaStream_t stream);
+
+cudaError_t launch_weight_map_compat(const float *faces, const int32_t *fim, float *wmap, int B,
+                                     int nf, int R, cudaStream_t stream);
+
+}  // namespace nr

@@ -1,0 +1,292 @@
+"""Host side of the rasterize path: same public functions as the reference's
+``neural_renderer_torch/rasterize.py`` (``rasterize_silhouettes`` :332-338, ``rasterize_rgba``
+:341-347, ``rasterize_rgb`` :350-356, ``rasterize_depth`` :359-365, ``rasterize_core`` :194-329),
+driving ONE fused CUDA forward and ONE fused CUDA backward through the C ABI instead of ~60
+torch ops with per-view host synchronisation.
+
+Differences from the reference that are deliberate (DESIGN.md "API notes"):
+  * ``hyperparams.image_size`` is NOT doubled in place when anti-aliasing is on
+    (the reference mutates the caller's object, rasterize.py:227-228);
+  * ``lights`` / ``backgrounds`` / ``background_color`` are outside the accelerated path
+    (lights are a "next" row; backgrounds are broken in the reference,
+    rasterize.py:156-159) and raise ``NotImplementedError``.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .rasterize_param import RasterizeParam, RasterizeHyperparam
+
+DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        # same error class and wording as CHECK_CUDA, rasterize_cuda.cpp:5
+        raise RuntimeError("%s must be a CUDA tensor" % name)
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i32c(t):
+    return t.detach().to(torch.int32).contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _Scratch:
+    """Per (device, stream) scratch: workspace bytes, pinned bin statistics, a CUDA event.
+    The (tile, face) pair capacity grows on demand and is remembered."""
+
+    _cache = {}
+
+    def __init__(self, device):
+        self.device = device
+        self.workspace = None
+        self.pair_capacity = 0
+        self.stats = torch.zeros(4, dtype=torch.int32).pin_memory()
+        ev = ctypes.c_void_p()
+        _lib.check(_lib.lib().nr_event_create(ctypes.byref(ev)), "nr_event_create")
+        self.event = ev
+
+    @classmethod
+    def get(cls, device, stream):
+        key = (device.index, stream)
+        s = cls._cache.get(key)
+        if s is None:
+            s = cls._cache[key] = cls(device)
+        return s
+
+    def ensure(self, cfg, capacity):
+        need = _lib.lib().nr_workspace_bytes(ctypes.byref(cfg), capacity)
+        if self.workspace is None or self.workspace.numel() < need:
+            # torch's caching allocator hands out 512-byte aligned blocks
+            self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        self.pair_capacity = capacity
+
+
+def _make_config(B, nv, nf, S, flags, hp, nvt=0, H=0, W=0):
+    return _lib.RasterConfig(batch=B, num_vertices=nv, num_faces=nf, image_size=S, flags=flags,
+                             near_plane=float(hp.near), far_plane=float(hp.far), eps=float(hp.eps),
+                             depth_min_delta=DEPTH_MIN_DELTA, num_tex_vertices=nvt, tex_height=H,
+                             tex_width=W)
+
+
+def _flags_of(hp):
+    return ((_lib.NR_DRAW_RGB if hp.draw_rgb else 0) |
+            (_lib.NR_DRAW_SILHOUETTES if hp.draw_silhouettes else 0) |
+            (_lib.NR_DRAW_DEPTH if hp.draw_depth else 0) |
+            (_lib.NR_DRAW_BACKSIDE if hp.draw_backside else 0) |
+            (_lib.NR_ANTI_ALIASING if hp.anti_aliasing else 0))
+
+
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
+    """Runs nr_rasterize_forward, regrowing the pair list if it overflowed.
+    Returns (images, internal, fim, wmap, dmap)."""
+    L = _lib.lib()
+    dev = vertices.device
+    B, S = cfg.batch, cfg.image_size
+    aa = bool(cfg.flags & _lib.NR_ANTI_ALIASING)
+    R = S * 2 if aa else S
+    C = L.nr_num_channels(cfg.flags)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sc = _Scratch.get(dev, stream)
+        fim = torch.empty((B, R, R), dtype=torch.int32, device=dev)
+        images = torch.empty((B, C, S, S), dtype=torch.float32, device=dev)
+        internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
+        wmap = torch.empty((B, R, R, 3), dtype=torch.float32, device=dev) if want_maps else None
+        dmap = torch.empty((B, R, R), dtype=torch.float32, device=dev) if want_maps else None
+        capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
+        for _ in range(4):
+            sc.ensure(cfg, capacity)
+            ws = sc.workspace
+            base = ws.data_ptr()
+            aligned = (base + 255) & ~255
+            rc = L.nr_rasterize_forward(
+                ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
+                _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal),
+                ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
+                ctypes.c_void_p(sc.stats.data_ptr()), sc.event, ctypes.c_void_p(stream))
+            _lib.check(rc, "nr_rasterize_forward")
+            # waits for the binning kernels only; the raster kernel is already queued behind them
+            _lib.check(L.nr_event_synchronize(sc.event), "nr_event_synchronize")
+            total, _max_tile, overflow, bad = sc.stats.tolist()
+            if bad:
+                raise IndexError("faces reference a vertex index outside [0, %d)" % cfg.num_vertices)
+            if not overflow:
+                return images, internal, fim, wmap, dmap
+            capacity = int(total * 1.25) + 4096
+        raise RuntimeError("tile pair list kept overflowing")
+
+
+class _Rasterize(torch.autograd.Function):
+    """Forward: nr_rasterize_forward. Backward: nr_rasterize_backward (Differentiation stencil +
+    every autograd edge the reference has on this path)."""
+
+    @staticmethod
+    def forward(ctx, vertices, vertices_textures, textures, faces, faces_textures, cfg):
+        v = _f32c(vertices)
+        vt = _f32c(vertices_textures) if vertices_textures is not None else None
+        tex = _f32c(textures) if textures is not None else None
+        images, internal, fim, _, _ = _forward_call(cfg, v, faces, vt, faces_textures, tex, False)
+        ctx.cfg = cfg
+        ctx.has_tex = tex is not None
+        saved = [v, faces, fim, internal if internal is not None else images]
+        if ctx.has_tex:
+            saved += [vt, faces_textures, tex]
+        ctx.save_for_backward(*saved)
+        return images
+
+    @staticmethod
+    def backward(ctx, grad_images):
+        cfg = ctx.cfg
+        L = _lib.lib()
+        if ctx.has_tex:
+            v, faces, fim, internal, vt, ft, tex = ctx.saved_tensors
+        else:
+            v, faces, fim, internal = ctx.saved_tensors
+            vt = ft = tex = None
+        g = _f32c(grad_images)
+        need_v, need_vt, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dev = v.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            gv = torch.zeros_like(v)
+            gvt = torch.zeros_like(vt) if (need_vt and vt is not None) else None
+            gtex = torch.zeros_like(tex) if (need_tex and tex is not None) else None
+            rc = L.nr_rasterize_backward(ctypes.byref(cfg), _ptr(v), _ptr(faces), _ptr(vt), _ptr(ft),
+                                         _ptr(tex), _ptr(fim), _ptr(internal), _ptr(g), _ptr(gv),
+                                         _ptr(gtex), _ptr(gvt), ctypes.c_void_p(stream))
+            _lib.check(rc, "nr_rasterize_backward")
+        return (gv if need_v else None), gvt, gtex, None, None, None
+
+
+def _prepare(vertices, faces, params, hyperparams):
+    # shape checks of rasterize.py:195-205 (AssertionError, like the reference)
+    assert vertices.ndim == 3
+    assert vertices.shape[2] == 3
+    assert faces.ndim == 2
+    assert faces.shape[1] == 3
+    _require_cuda(vertices, "vertices")
+    if params.lights is not None:
+        raise NotImplementedError("lights are outside the accelerated path (SURVEY.md section 8f)")
+    if params.backgrounds is not None or params.background_color is not None:
+        raise NotImplementedError("backgrounds are outside the accelerated path (and broken in the "
+                                  "reference, rasterize.py:156-159)")
+    dev = vertices.device
+    faces_d = _i32c(torch.as_tensor(faces)).to(dev)
+    B, nv = vertices.shape[:2]
+    nf = faces_d.shape[0]
+    vt = ft = tex = None
+    nvt = H = W = 0
+    if hyperparams.draw_rgb:
+        assert params.vertices_textures.ndim == 3
+        assert params.vertices_textures.shape[2] == 2
+        assert params.faces_textures.ndim == 2
+        assert params.faces_textures.shape[1] == 3
+        assert params.textures.ndim == 4
+        assert params.textures.shape[1] == 3
+        vt, tex = params.vertices_textures, params.textures
+        _require_cuda(vt, "vertices_textures")
+        _require_cuda(tex, "textures")
+        assert vt.shape[0] == B and tex.shape[0] == B
+        assert params.faces_textures.shape[0] == nf
+        ft = _i32c(torch.as_tensor(params.faces_textures)).to(dev)
+        nvt, H, W = vt.shape[1], tex.shape[2], tex.shape[3]
+    cfg = _make_config(B, nv, nf, int(hyperparams.image_size), _flags_of(hyperparams), hyperparams,
+                       nvt, H, W)
+    return cfg, faces_d, vt, ft, tex
+
+
+def rasterize_core(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    """``rasterize.py:194-329``. vertices [B,nv,3] screen space, faces [nf,3] -> images [B,C,S,S]."""
+    cfg, faces_d, vt, ft, tex = _prepare(vertices, faces, params, hyperparams)
+    return _Rasterize.apply(vertices, vt, tex, faces_d, ft, cfg)
+
+
+def rasterize_maps(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    """Non-differentiable view of the internal maps the reference builds inside rasterize_core
+    (``face_index_map`` :235, ``weight_map`` :236, depth :292) plus the images.  Test / debug aid."""
+    cfg, faces_d, vt, ft, tex = _prepare(vertices, faces, params, hyperparams)
+    with torch.no_grad():
+        images, internal, fim, wmap, dmap = _forward_call(
+            cfg, _f32c(vertices), faces_d, _f32c(vt) if vt is not None else None, ft,
+            _f32c(tex) if tex is not None else None, True)
+    return dict(images=images, internal_images=internal if internal is not None else images,
+                face_index_map=fim, weight_map=wmap, depth_map=dmap)
+
+
+def rasterize_silhouettes(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    hyperparams.draw_rgb = False
+    hyperparams.draw_silhouettes = True
+    hyperparams.draw_depth = False
+    return rasterize_core(vertices, faces, params, hyperparams)[:, 0]
+
+
+def rasterize_rgba(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    hyperparams.draw_rgb = True
+    hyperparams.draw_silhouettes = True
+    hyperparams.draw_depth = False
+    return rasterize_core(vertices, faces, params, hyperparams)
+
+
+def rasterize_rgb(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    hyperparams.draw_rgb = True
+    hyperparams.draw_silhouettes = False
+    hyperparams.draw_depth = False
+    return rasterize_core(vertices, faces, params, hyperparams)
+
+
+def rasterize_depth(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
+    hyperparams.draw_rgb = False
+    hyperparams.draw_silhouettes = False
+    hyperparams.draw_depth = True
+    return rasterize_core(vertices, faces, params, hyperparams)[:, 0]
+
+
+# ------------------------------------------------------------------------------------------------
+# The two operators of the reference's pybind module, same names and argument order
+# (cuda/rasterize_cuda.cpp:55-65, :81-90; called from rasterize.py:34-35 and :75).
+
+def face_index_map_forward_safe(faces, face_index, num_faces, image_size, near, far, draw_backside,
+                                eps, depth_min_delta):
+    """faces [B,nf,3,3] CUDA f32 contiguous; face_index [B*S*S] CUDA i32, written in place and returned."""
+    _require_cuda(faces, "faces")
+    _require_cuda(face_index, "face_index")
+    if not faces.is_contiguous():
+        raise RuntimeError("faces must be contiguous")
+    if not face_index.is_contiguous():
+        raise RuntimeError("face_index must be contiguous")
+    if faces.dtype != torch.float32 or face_index.dtype != torch.int32:
+        raise RuntimeError("faces must be float32 and face_index int32")
+    with torch.cuda.device(faces.device):
+        stream = torch.cuda.current_stream(faces.device).cuda_stream
+        rc = _lib.lib().nr_face_index_map_forward_safe(
+            _ptr(faces), _ptr(face_index), faces.shape[0], int(num_faces), int(image_size), float(near),
+            float(far), int(draw_backside), float(eps), float(depth_min_delta), ctypes.c_void_p(stream))
+    _lib.check(rc, "face_index_map_forward_safe")
+    return face_index
+
+
+def compute_weight_map_c(faces, face_index_map, weight_map, num_faces, image_size):
+    """faces [B,nf,3,3], face_index_map flat i32, weight_map [B*S*S,3] zeros written in place.
+    Returns face_index_map like the reference (rasterize_cuda_kernel.cu:440)."""
+    for t, n in ((faces, "faces"), (face_index_map, "face_index_map"), (weight_map, "weight_map")):
+        _require_cuda(t, n)
+        if not t.is_contiguous():
+            raise RuntimeError("%s must be contiguous" % n)
+    with torch.cuda.device(faces.device):
+        stream = torch.cuda.current_stream(faces.device).cuda_stream
+        rc = _lib.lib().nr_compute_weight_map(_ptr(faces), _ptr(face_index_map), _ptr(weight_map),
+                                              faces.shape[0], int(num_faces), int(image_size),
+                                              ctypes.c_void_p(stream))
+    _lib.check(rc, "compute_weight_map_c")
+    return face_index_map

@@ -1,0 +1,339 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (BASELINE.json north_star):
+  * face_index_map: bit-exact;
+  * weight_map / depth_map / images: the forward replays the reference arithmetic operation by
+    operation, so they are compared with atol 1e-6 (images) and exactly (weight map);
+  * gradients: |d| <= 1e-5 * |ref| + 1e-5 * max|ref|  (sums of thousands of float32 terms whose
+    order differs between atomics, index_put and the CPU oracle; the reference's own CUDA
+    index_put has the same run-to-run noise).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import pipeline as ref
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "case_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def nr():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import neural_renderer_v2_pytorch_b200 as nr_
+    return nr_
+
+
+def grad_close(got, want, what):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.abs(want).max()
+    tol = 1e-5 * np.abs(want) + 1e-5 * scale
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), "%s: %d / %d beyond tolerance, max |d| = %.3g (scale %.3g)" % (
+        what, bad.sum(), bad.size, np.abs(got - want).max(), scale)
+
+
+def run_cuda(nr, d, dev="cuda:0"):
+    mode = str(d["mode"])
+    hp = nr.RasterizeHyperparam(image_size=int(d["image_size"]), near=float(d["near"]), far=float(d["far"]),
+                                anti_aliasing=bool(d["anti_aliasing"]), draw_backside=bool(d["draw_backside"]))
+    v = torch.from_numpy(d["vertices"]).to(dev).requires_grad_(True)
+    faces = torch.from_numpy(d["faces"]).to(dev)
+    tex = vt = None
+    if mode in ("rgb", "rgba"):
+        tex = torch.from_numpy(d["textures"]).to(dev).requires_grad_(True)
+        vt = torch.from_numpy(d["vertices_textures"]).to(dev).requires_grad_(True)
+        p = nr.RasterizeParam(vertices_textures=vt, faces_textures=torch.from_numpy(d["faces_textures"]).to(dev),
+                              textures=tex)
+    else:
+        p = nr.RasterizeParam()
+    fn = {"silhouettes": nr.rasterize_silhouettes, "rgb": nr.rasterize_rgb, "rgba": nr.rasterize_rgba,
+          "depth": nr.rasterize_depth}[mode]
+    images = fn(v, faces, p, hp)
+    (images * torch.from_numpy(d["grad_images"]).to(dev)).sum().backward()
+    hp2 = nr.RasterizeHyperparam(image_size=int(d["image_size"]), near=float(d["near"]), far=float(d["far"]),
+                                 anti_aliasing=bool(d["anti_aliasing"]), draw_backside=bool(d["draw_backside"]),
+                                 draw_rgb=mode in ("rgb", "rgba"), draw_silhouettes=mode in ("silhouettes", "rgba"),
+                                 draw_depth=mode == "depth")
+    maps = nr.rasterize_maps(v.detach(), faces, p, hp2)
+    return images, v, tex, vt, maps
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_case(nr, name):
+    """CUDA path vs fixtures produced by the reference's own Python code (tests/golden/make_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    images, v, tex, vt, maps = run_cuda(nr, d)
+    if "face_index_map" in d:
+        assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"]), "face_index_map not bit-exact"
+        assert np.array_equal(maps["weight_map"].cpu().numpy(), d["weight_map"]), "weight_map differs"
+    np.testing.assert_allclose(images.detach().cpu().numpy(), d["images"], rtol=1e-5, atol=1e-6)
+    grad_close(v.grad.cpu().numpy(), d["grad_vertices"], "grad_vertices")
+    if tex is not None:
+        grad_close(tex.grad.cpu().numpy(), d["grad_textures"], "grad_textures")
+        grad_close(vt.grad.cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
+
+
+def test_renderer_end_to_end(nr):
+    """World-space vertices -> look_at -> perspective -> rasterize_rgba with AA, gradients back to
+    world vertices and textures, vs the reference's Renderer.render run on CPU."""
+    d = np.load(os.path.join(GOLDEN, "renderer_rgba_aa_32.npz"))
+    dev = "cuda:0"
+    r = nr.Renderer()
+    r.image_size = int(d["image_size"])
+    r.viewpoints = torch.from_numpy(d["viewpoints"]).to(dev)
+    vw = torch.from_numpy(d["vertices_world"]).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(d["textures"]).to(dev).requires_grad_(True)
+    images = r.render(vw, torch.from_numpy(d["faces"]).to(dev), torch.from_numpy(d["vertices_textures"]).to(dev),
+                      torch.from_numpy(d["faces_textures"]).to(dev), tex)
+    (images * torch.from_numpy(d["grad_images"]).to(dev)).sum().backward()
+    # look_at / perspective run as torch CUDA ops here and torch CPU ops in the fixture: a vertex
+    # that moves by 1 ulp can flip a pixel, so allow a handful of differing pixels
+    diff = np.abs(images.detach().cpu().numpy() - d["images"])
+    assert (diff > 1e-4).mean() < 2e-3, "too many differing pixels: %g" % (diff > 1e-4).mean()
+    gv, gw = vw.grad.cpu().numpy(), d["grad_vertices_world"]
+    assert np.abs(gv - gw).max() <= 2e-2 * np.abs(gw).max()
+
+
+def _fim_cuda(nr, faces_np, R, near=0.1, far=100.0, backside=True):
+    f = torch.from_numpy(np.ascontiguousarray(faces_np, dtype=np.float32)).cuda()
+    B, nf = f.shape[:2]
+    fim = torch.full((B * R * R,), -7, dtype=torch.int32, device="cuda")
+    out = nr.face_index_map_forward_safe(f, fim, nf, R, near, far, int(backside), 1e-8, 1e-4)
+    assert out.data_ptr() == fim.data_ptr()
+    wm = torch.zeros((B * R * R, 3), dtype=torch.float32, device="cuda")
+    nr.compute_weight_map_c(f, fim, wm, nf, R)
+    return fim.reshape(B, R, R).cpu().numpy(), wm.reshape(B, R, R, 3).cpu().numpy()
+
+
+def _check_vs_oracle(nr, faces_np, R, **kw):
+    fim, wm = _fim_cuda(nr, faces_np, R, **kw)
+    want = oracle.face_index_map(faces_np, R, kw.get("near", 0.1), kw.get("far", 100.0), kw.get("backside", True))
+    nbad = int((fim != want).sum())
+    assert nbad == 0, "face_index_map: %d / %d pixels differ" % (nbad, fim.size)
+    assert np.array_equal(wm, oracle.weight_map(faces_np, want)), "weight_map differs"
+    return fim
+
+
+def random_triangles(B, nf, seed, size=0.05, zlo=1.0, zhi=3.0):
+    rng = np.random.RandomState(seed)
+    c = rng.uniform(-1.1, 1.1, size=(B, nf, 1, 2))
+    xy = c + rng.normal(0, size, size=(B, nf, 3, 2))
+    z = rng.uniform(zlo, zhi, size=(B, nf, 1, 1)) + rng.normal(0, 0.02, size=(B, nf, 3, 1))
+    return np.concatenate([xy, z], -1).astype(np.float32)
+
+
+@pytest.mark.parametrize("R", [16, 64, 100, 250, 256])
+def test_random_small_triangles(nr, R):
+    """Reference-signature operators vs the C oracle; R = 100 / 250 exercise partial tiles."""
+    _check_vs_oracle(nr, random_triangles(2, 3000, R), R)
+
+
+def test_random_small_triangles_cull(nr):
+    _check_vs_oracle(nr, random_triangles(2, 3000, 5), 128, backside=False)
+
+
+def test_large_triangles_cover_every_tile(nr):
+    """Faces spanning the whole screen land in every tile list (many tiles per face)."""
+    f = random_triangles(2, 200, 11, size=1.5)
+    _check_vs_oracle(nr, f, 128)
+
+
+def test_hysteresis_is_order_dependent(nr):
+    """Three coplanar-ish full-screen faces 5e-5 apart in depth: the reference's sequential
+    z-test (rasterize_cuda_kernel.cu:145) keeps the FIRST face in index order unless a later one
+    is closer by more than 1e-4; a (min depth, min index) rule would give a different answer."""
+    def quad(z):
+        return [[-2., -2., z], [2., -2., z], [0., 2., z]]
+    a = np.array([[quad(1.0), quad(0.99995), quad(0.9999)]], np.float32)
+    b = np.array([[quad(0.9999), quad(0.99995), quad(1.0)]], np.float32)
+    c = np.array([[quad(1.0), quad(0.9998), quad(0.99975)]], np.float32)
+    for faces_np in (a, b, c):
+        _check_vs_oracle(nr, faces_np, 32)
+    fim_a = _check_vs_oracle(nr, a, 32)
+    fim_c = _check_vs_oracle(nr, c, 32)
+    assert set(np.unique(fim_a)) <= {-1, 0, 2} and set(np.unique(fim_c)) <= {-1, 1}
+
+
+def test_duplicate_and_degenerate_faces(nr):
+    f = random_triangles(1, 500, 3, size=0.2)
+    f = np.concatenate([f, f[:, :100]], 1)          # exact duplicates later in the list never win
+    f[0, 7] = f[0, 7, 0]                             # zero-area face
+    f[0, 8, :, :2] = np.array([[0, 0], [0.5, 0.5], [1, 1]], np.float32)   # collinear
+    _check_vs_oracle(nr, f, 96)
+
+
+def test_non_finite_vertices(nr):
+    f = random_triangles(1, 400, 4, size=0.3)
+    f[0, 3, 0, 0] = np.nan
+    f[0, 9, 1, 1] = np.inf
+    f[0, 15, 2, 0] = -np.inf
+    f[0, 21, 0, 2] = np.nan      # NaN depth: stays in the lists, never wins
+    f[0, 27, 1, 2] = np.inf      # infinite depth at one corner: finite zp, can win
+    f[0, 33, 2, 2] = 0.0         # z = 0
+    f[0, 39, :, 2] = -1.0        # behind the camera
+    _check_vs_oracle(nr, f, 96)
+
+
+def test_near_far_clipping(nr):
+    f = random_triangles(2, 2000, 6, size=0.1, zlo=0.05, zhi=4.0)
+    _check_vs_oracle(nr, f, 128, near=1.0, far=2.5)
+
+
+def test_long_tile_lists(nr):
+    """> 1024 faces in one tile: global-memory sort path and multi-chunk staging."""
+    rng = np.random.RandomState(8)
+    f = random_triangles(1, 5000, 8, size=0.02)
+    f[..., :2] = f[..., :2] * 0.05 + rng.uniform(-0.02, 0.02)     # everything inside one tile
+    _check_vs_oracle(nr, f, 64)
+
+
+def test_teapot_views(nr):
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    B = 4
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    g = torch.Generator().manual_seed(5)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20,
+                                    torch.rand(B, generator=g) * 360)
+    vs = nr.perspective(nr.look_at(vw, eye))
+    faces_np = vs[:, torch.from_numpy(d["faces"]).long()].numpy()
+    _check_vs_oracle(nr, faces_np, 256)
+    vs[1] = 0                    # an all-zero view, as in tests_torch/test_rasterize.py:21-23
+    _check_vs_oracle(nr, vs[:, torch.from_numpy(d["faces"]).long()].numpy(), 128)
+
+
+def test_empty_inputs(nr):
+    """No faces / everything off-screen -> all background."""
+    fim, wm = _fim_cuda(nr, np.zeros((2, 1, 3, 3), np.float32), 32)
+    assert (fim == -1).all() and (wm == 0).all()
+    f = random_triangles(1, 50, 2) + np.array([5., 5., 0.], np.float32)
+    fim, _ = _fim_cuda(nr, f, 32)
+    assert (fim == -1).all()
+
+
+def test_fused_matches_oracle_pipeline_midsize(nr):
+    """Fused forward + backward vs the torch-CPU oracle at 128^2, RGBA + depth in one call."""
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    B, S, ts = 3, 128, 3
+    g = torch.Generator().manual_seed(42)
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20,
+                                    torch.rand(B, generator=g) * 360)
+    vs = nr.perspective(nr.look_at(vw, eye))
+    faces = torch.from_numpy(d["faces"])
+    vt_np, ft_np, tex_np = nr.create_textures(faces.shape[0], ts)
+    tex0 = torch.rand((B,) + tex_np.shape, generator=g)
+    vt0 = torch.from_numpy(vt_np)[None].repeat(B, 1, 1)
+    G = torch.randn((B, 5, S, S), generator=g)
+
+    v0 = vs.clone().requires_grad_(True)
+    t0 = tex0.clone().requires_grad_(True)
+    img0 = ref.rasterize(v0, faces, S, False, draw_rgb=True, draw_silhouettes=True, draw_depth=True,
+                         vertices_textures=vt0, faces_textures=ft_np, textures=t0)
+    (img0 * G).sum().backward()
+
+    v1 = vs.clone().cuda().requires_grad_(True)
+    t1 = tex0.clone().cuda().requires_grad_(True)
+    hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=False, draw_rgb=True, draw_silhouettes=True,
+                                draw_depth=True)
+    p = nr.RasterizeParam(vertices_textures=vt0.cuda(), faces_textures=torch.from_numpy(ft_np).cuda(), textures=t1)
+    img1 = nr.rasterize_core(v1, faces.cuda(), p, hp)
+    (img1 * G.cuda()).sum().backward()
+    np.testing.assert_allclose(img1.detach().cpu().numpy(), img0.detach().numpy(), rtol=1e-5, atol=1e-6)
+    grad_close(v1.grad.cpu().numpy(), v0.grad.numpy(), "grad_vertices")
+    grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
+
+
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_differentiation_known_answer(nr, C):
+    """Standalone differentiation() op vs the reference's Differentiation.backward output."""
+    d = np.load(os.path.join(GOLDEN, "diff_known_answer_c%d.npz" % C))
+    images = torch.from_numpy(d["images"]).cuda()
+    coords = torch.zeros(images.shape[:3] + (2,), device="cuda", requires_grad=True)
+    out = nr.differentiation(images, coords)
+    assert torch.equal(out, images)
+    (out * torch.from_numpy(d["grad_output"]).cuda()).sum().backward()
+    np.testing.assert_allclose(coords.grad.cpu().numpy(), d["grad_coordinates"], rtol=1e-5, atol=1e-5)
+
+
+def test_differentiation_binary_image(nr):
+    d = np.load(os.path.join(GOLDEN, "diff_known_answer_binary.npz"))
+    images = torch.from_numpy(d["images"]).cuda()
+    coords = torch.zeros(images.shape[:3] + (2,), device="cuda", requires_grad=True)
+    (nr.differentiation(images, coords) * torch.from_numpy(d["grad_output"]).cuda()).sum().backward()
+    np.testing.assert_allclose(coords.grad.cpu().numpy(), d["grad_coordinates"], rtol=1e-5, atol=1e-5)
+
+
+def test_differentiation_finite_difference_property(nr):
+    """The reference's own known-answer check (tests_torch/test_differentiation.py:31-65): |grad| equals
+    the one-pixel-shift finite difference, rtol 1e-4."""
+    rng = np.random.RandomState(0)
+    B, S = 4, 32
+    images = torch.from_numpy(rng.normal(size=(B, S, S, 3)).astype("float32")).cuda()
+    noise = torch.from_numpy(rng.normal(size=(B, S, S, 3)).astype("float32")).cuda()
+    coords = torch.zeros((B, S, S, 2), device="cuda", requires_grad=True)
+    (nr.differentiation(images, coords) * noise).sum().backward()
+    g = coords.grad
+    step = 2. / S
+    for _ in range(50):
+        yi, xi = rng.randint(1, S - 1), rng.randint(1, S - 1)
+        for axis, col in ((1, 1), (2, 0)):
+            def shifted(sign):
+                im = images.clone()
+                if axis == 1:
+                    im[:, yi - sign, xi] = images[:, yi, xi]
+                    im[:, yi, xi] = images[:, yi + sign, xi]
+                else:
+                    im[:, yi, xi - sign] = images[:, yi, xi]
+                    im[:, yi, xi] = images[:, yi, xi + sign]
+                gg = ((im - images) * noise).sum((1, 2, 3)) / step
+                return torch.min(gg, torch.zeros_like(gg))
+            want = torch.max(shifted(1).abs(), shifted(-1).abs())
+            assert torch.allclose(want, g[:, yi, xi, col].abs(), rtol=1e-4, atol=1e-5)
+
+
+def test_errors(nr):
+    hp = nr.RasterizeHyperparam(image_size=32, anti_aliasing=False)
+    v = torch.zeros(1, 3, 3)
+    f = torch.tensor([[0, 1, 2]], dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        nr.rasterize_silhouettes(v, f, nr.RasterizeParam(), hp)
+    with pytest.raises(AssertionError):
+        nr.rasterize_silhouettes(v.cuda()[0], f, nr.RasterizeParam(), hp)
+    with pytest.raises(IndexError):
+        nr.rasterize_silhouettes(v.cuda(), torch.tensor([[0, 1, 9]], dtype=torch.int32), nr.RasterizeParam(), hp)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        nr.face_index_map_forward_safe(torch.zeros(1, 9, 1, device="cuda").permute(0, 2, 1).reshape(1, 1, 3, 3).transpose(2, 3),
+                                       torch.zeros(32 * 32, dtype=torch.int32, device="cuda"), 1, 32, 0.1, 100., 1, 1e-8, 1e-4)
+
+
+def test_square_optimisation_converges(nr):
+    """tests_torch/test_rasterize.py:205-249 in spirit: a 2-triangle square must be pulled onto a target
+    silhouette by Adam using the approximate gradients (IoU loss < 0.05 within 300 steps)."""
+    dev = "cuda:0"
+    S = 64
+    target = torch.zeros(S, S, device=dev)
+    target[16:40, 24:56] = 1.
+    vertices = torch.tensor([[0.1, 0.1, 1.], [-0.1, 0.1, 1.], [-0.1, -0.1, 1.], [0.1, -0.1, 1.]], device=dev)
+    vertices = torch.nn.Parameter(vertices)
+    faces = torch.tensor([[0, 1, 2], [0, 2, 3]], dtype=torch.int32, device=dev)
+    opt = torch.optim.Adam([vertices], lr=0.01)
+    loss = None
+    for _ in range(300):
+        hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=False)
+        image = nr.rasterize_silhouettes(vertices[None], faces, nr.RasterizeParam(), hp)[0]
+        loss = 1 - torch.sum(image * target) / torch.sum(image + target - image * target)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if float(loss) < 0.05:
+            break
+    assert float(loss) < 0.05, "did not converge: %g" % float(loss)
