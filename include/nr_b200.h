@@ -98,6 +98,17 @@ NR_API int nr_event_create(void **event);
 NR_API int nr_event_destroy(void *event);
 NR_API int nr_event_synchronize(void *event);
 
+/*
+ * Per-kernel timing hook for bench.py: while enabled, every kernel this library launches is
+ * bracketed by CUDA events on its launch stream.  nr_profile_collect synchronises those events and
+ * ADDS the elapsed milliseconds / launch counts per slot into ms[NR_PROF_SLOTS] / launches[...]
+ * (slots: 0 memset, 1 setup_count, 2 scan_tiles, 3 scatter, 4 sort_long, 5 raster, 6 backward,
+ * 7 differentiation_backward, 8 weight_map_compat), then forgets them.
+ */
+#define NR_PROF_SLOTS 9
+NR_API int nr_profile_enable(int on);
+NR_API int nr_profile_collect(float *ms, int32_t *launches);
+
 /* Bytes of scratch the forward needs for `pair_capacity` (tile, face) pairs. */
 NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity);
 

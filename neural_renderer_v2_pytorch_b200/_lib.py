@@ -28,7 +28,11 @@ SYMBOLS = (
     "nr_abi_version", "nr_last_error", "nr_num_channels", "nr_event_create", "nr_event_destroy",
     "nr_event_synchronize", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
     "nr_differentiation_backward", "nr_face_index_map_forward_safe", "nr_compute_weight_map",
+    "nr_profile_enable", "nr_profile_collect",
 )
+NR_PROF_SLOTS = 9
+PROF_SLOT_NAMES = ("memset", "setup_count", "scan_tiles", "scatter", "sort_long", "raster", "backward",
+                   "differentiation_backward", "weight_map_compat")
 
 
 class RasterConfig(ctypes.Structure):
@@ -104,6 +108,10 @@ def lib():
     L.nr_face_index_map_forward_safe.argtypes = [vp, vp, i32, i32, i32, f32, f32, i32, f32, f32, vp]
     L.nr_compute_weight_map.restype = ctypes.c_int
     L.nr_compute_weight_map.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.nr_profile_enable.restype = ctypes.c_int
+    L.nr_profile_enable.argtypes = [ctypes.c_int]
+    L.nr_profile_collect.restype = ctypes.c_int
+    L.nr_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     if L.nr_abi_version() != 1:
         raise RuntimeError("libnr_b200.so ABI version mismatch")
     _lib = L

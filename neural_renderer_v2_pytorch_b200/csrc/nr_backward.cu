@@ -266,6 +266,7 @@ k_differentiation_backward(const float *__restrict__ images, const float *__rest
 cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     dim3 grid(a.ntx * a.ntx, a.B);
+    ProfScope p(PROF_BACKWARD, stream);
     k_backward<<<grid, TILE_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
@@ -275,6 +276,7 @@ cudaError_t launch_differentiation_backward(const float *images, const float *gr
                                             cudaStream_t stream) {
     const long long total = (long long)B * R * R;
     if (total <= 0) return cudaSuccess;
+    ProfScope p(PROF_DIFF_BACKWARD, stream);
     k_differentiation_backward<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
         images, grad_output, grad_coordinates, B, R, C);
     return cudaGetLastError();

@@ -226,20 +226,32 @@ k_sort_long(const int *__restrict__ tile_count, const int *__restrict__ tile_off
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
     const int nt = a.ntx * a.ntx;
     // header + tile counts are contiguous in the workspace: one memset
-    cudaError_t e = cudaMemsetAsync(a.hdr, 0, sizeof(BinHeader) + sizeof(int) * (size_t)a.B * nt, stream);
+    cudaError_t e;
+    {
+        ProfScope p(PROF_MEMSET, stream);
+        e = cudaMemsetAsync(a.hdr, 0, sizeof(BinHeader) + sizeof(int) * (size_t)a.B * nt, stream);
+    }
     if (e != cudaSuccess) return e;
     const long long nface = (long long)a.B * a.nf;
     if (nface > 0) {
         const unsigned blocks = (unsigned)((nface + 255) / 256);
+        ProfScope p(PROF_SETUP, stream);
         k_setup_count<<<blocks, 256, 0, stream>>>(a.verts, a.faces, a.B, a.nv, a.nf, a.R,
                                                   a.draw_backside, a.rec, a.tile_count, a.ntx, a.hdr);
     }
-    k_scan_tiles<<<a.B, 1024, 0, stream>>>(a.tile_count, a.tile_offset, a.tile_cursor, nt,
-                                           a.pair_capacity, a.hdr);
+    {
+        ProfScope p(PROF_SCAN, stream);
+        k_scan_tiles<<<a.B, 1024, 0, stream>>>(a.tile_count, a.tile_offset, a.tile_cursor, nt,
+                                               a.pair_capacity, a.hdr);
+    }
     if (nface > 0) {
         const unsigned blocks = (unsigned)((nface + 255) / 256);
-        k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_cursor, a.pairs,
-                                              a.pair_capacity, a.hdr);
+        {
+            ProfScope p(PROF_SCATTER, stream);
+            k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_cursor, a.pairs,
+                                                  a.pair_capacity, a.hdr);
+        }
+        ProfScope p(PROF_SORT_LONG, stream);
         k_sort_long<<<a.sm_count * 2, 256, 0, stream>>>(a.tile_count, a.tile_offset, a.B * nt, a.pairs,
                                                         SMEM_SORT_CAP, a.hdr);
     }

@@ -8,6 +8,19 @@ namespace nr {
 // longer ones by k_sort_long in global memory.
 constexpr int SMEM_SORT_CAP = 1024;
 
+// Brackets one launch with CUDA events while nr_profile_enable(1) is in force (nr_profile.cu).
+enum ProfSlot { PROF_MEMSET = 0, PROF_SETUP, PROF_SCAN, PROF_SCATTER, PROF_SORT_LONG, PROF_RASTER,
+                PROF_BACKWARD, PROF_DIFF_BACKWARD, PROF_WEIGHT_MAP };
+class ProfScope {
+public:
+    ProfScope(int slot, cudaStream_t stream);
+    ~ProfScope();
+private:
+    int slot_;
+    cudaStream_t stream_;
+    void *start_;
+};
+
 struct BinningArgs {
     const float *verts;
     const int32_t *faces;   // may be null: face f = vertices 3f..3f+2

@@ -287,6 +287,7 @@ k_weight_map_compat(const float *__restrict__ faces, const int32_t *__restrict__
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     dim3 grid(a.ntx * a.ntx, a.B);
+    ProfScope p(PROF_RASTER, stream);
     k_raster<<<grid, TILE_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
@@ -295,6 +296,7 @@ cudaError_t launch_weight_map_compat(const float *faces, const int32_t *fim, flo
                                      int nf, int R, cudaStream_t stream) {
     const long long total = (long long)B * R * R;
     if (total <= 0) return cudaSuccess;
+    ProfScope p(PROF_WEIGHT_MAP, stream);
     k_weight_map_compat<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(faces, fim, wmap, total, nf, R);
     return cudaGetLastError();
 }
