@@ -131,6 +131,10 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   images_internal     [B, C, R, R] out, required with NR_ANTI_ALIASING (the backward
  *                                    stencil runs at internal resolution), else may be NULL
  *                                    (then `images` itself is the internal image)
+ *   tile_list           [4 + 4 * B * ceil(R/16)^2] i32 out, optional, 16-byte aligned: element 0 =
+ *                       number of non-empty 16x16 tiles, then 4 ints per tile (view, tile_x |
+ *                       tile_y << 16, list offset, list length).  Pass it to
+ *                       nr_rasterize_backward so the backward visits only those tiles.
  *   workspace           nr_workspace_bytes(cfg, pair_capacity) bytes, 256-byte aligned
  *   stats_host          optional pinned host nrBinStats
  *   stats_event         optional cudaEvent_t (as void*, e.g. from nr_event_create) recorded right
@@ -140,9 +144,9 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
 NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,
                          const float *textures, int32_t *face_index_map, float *weight_map,
-                         float *depth_map, float *images, float *images_internal, void *workspace,
-                         size_t workspace_bytes, int64_t pair_capacity, nrBinStats *stats_host,
-                         void *stats_event, void *stream);
+                         float *depth_map, float *images, float *images_internal, int32_t *tile_list,
+                         void *workspace, size_t workspace_bytes, int64_t pair_capacity,
+                         nrBinStats *stats_host, void *stats_event, void *stream);
 
 /*
  * Fused backward: AA / flip / permute backward, the Differentiation stencil
@@ -152,6 +156,7 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
  *
  *   face_index_map      [B, R, R]    from the forward
  *   images_internal     [B, C, R, R] from the forward (pass `images` when not anti-aliased)
+ *   tile_list           from the forward, or NULL (then every tile is visited)
  *   grad_images         [B, C, S, S] upstream gradient
  *   grad_vertices       [B, nv, 3]   out, ACCUMULATED into (caller zero-fills)
  *   grad_textures       [B, 3, H, W] out, accumulated, optional
@@ -160,8 +165,8 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
 NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
                           const float *textures, const int32_t *face_index_map,
-                          const float *images_internal, const float *grad_images,
-                          float *grad_vertices, float *grad_textures,
+                          const float *images_internal, const int32_t *tile_list,
+                          const float *grad_images, float *grad_vertices, float *grad_textures,
                           float *grad_vertices_textures, void *stream);
 
 /*

@@ -99,9 +99,9 @@ def lib():
     L.nr_workspace_bytes.argtypes = [ctypes.POINTER(RasterConfig), i64]
     L.nr_rasterize_forward.restype = ctypes.c_int
     L.nr_rasterize_forward.argtypes = [ctypes.POINTER(RasterConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, vp, ctypes.c_size_t, i64, vp, vp, vp]
+                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, vp]
     L.nr_rasterize_backward.restype = ctypes.c_int
-    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 12
+    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 13
     L.nr_differentiation_backward.restype = ctypes.c_int
     L.nr_differentiation_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.nr_face_index_map_forward_safe.restype = ctypes.c_int

@@ -27,6 +27,7 @@ struct Carve {
     int *tile_count, *tile_offset, *tile_cursor;
     nr::FaceRec *rec;
     int32_t *pairs;
+    int32_t *tile_list;
     size_t bytes;
 };
 
@@ -49,6 +50,8 @@ Carve carve(void *base, int B, int nf, int R, long long pair_capacity) {
     off = align256(off + (size_t)B * nf * sizeof(nr::FaceRec));
     c.pairs = (int32_t *)(p + off);
     off = align256(off + (size_t)(pair_capacity > 0 ? pair_capacity : 1) * sizeof(int32_t));
+    c.tile_list = (int32_t *)(p + off);
+    off = align256(off + (nr::TILE_LIST_HDR + nr::TILE_ENTRY_INTS * nt) * sizeof(int32_t));
     c.bytes = off;
     return c;
 }
@@ -128,9 +131,9 @@ size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
 int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,
                          const float *textures, int32_t *face_index_map, float *weight_map,
-                         float *depth_map, float *images, float *images_internal, void *workspace,
-                         size_t workspace_bytes, int64_t pair_capacity, nrBinStats *stats_host,
-                         void *stats_event, void *stream_) {
+                         float *depth_map, float *images, float *images_internal, int32_t *tile_list,
+                         void *workspace, size_t workspace_bytes, int64_t pair_capacity,
+                         nrBinStats *stats_host, void *stats_event, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
@@ -165,6 +168,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.pairs = c.pairs;
     ba.pair_capacity = pair_capacity;
     ba.hdr = c.hdr;
+    ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
     cudaError_t e = nr::launch_binning(ba, stream);
     if (e != cudaSuccess) return fail_cuda(e, "binning");
@@ -183,6 +187,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.tile_offset = c.tile_offset;
     ra.pairs = c.pairs;
     ra.hdr = c.hdr;
+    ra.tile_list = ba.tile_list;
+    ra.sm_count = ba.sm_count;
     ra.B = cfg->batch;
     ra.nf = cfg->num_faces;
     ra.R = R;
@@ -213,8 +219,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
 int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
                           const float *textures, const int32_t *face_index_map,
-                          const float *images_internal, const float *grad_images,
-                          float *grad_vertices, float *grad_textures,
+                          const float *images_internal, const int32_t *tile_list,
+                          const float *grad_images, float *grad_vertices, float *grad_textures,
                           float *grad_vertices_textures, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
@@ -232,6 +238,8 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
     a.fim = face_index_map;
     a.internal = images_internal;
     a.grad_images = grad_images;
+    a.tile_list = tile_list;
+    a.sm_count = sm_count_cached();
     a.grad_verts = grad_vertices;
     a.grad_tex = grad_textures;
     a.grad_vt = grad_vertices_textures;
@@ -308,7 +316,7 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
         }
         s.pair_capacity = cap;
         int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
-                                      nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, stream);
+                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, stream);
         if (rc != NR_OK) return rc;
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");

@@ -83,14 +83,13 @@ __device__ __forceinline__ void clamp_shares(float x0, float lo, float hi, float
     slo = s1 * (1.f - sa);
 }
 
-// Backward of sample_texture(): scatters the four bilinear taps into grad_tex (planar
-// [3, H, W] of this view) and returns the gradients w.r.t. face depths and corner uv's.
-__device__ __forceinline__ void sample_texture_backward(const float *__restrict__ tex_b,
-                                                        float *__restrict__ gtex_b, int H, int W,
+// Backward of sample_texture(): returns the four tap indices (-1 when the tap reads as zero),
+// the tap weights, and the gradients w.r.t. face depths and corner uv's.
+__device__ __forceinline__ void sample_texture_backward(const float *__restrict__ tex_b, int H, int W,
                                                         float eps, const float q[3], const float z[3],
                                                         const float u[3], const float v[3],
-                                                        const float g[3], float gz[3], float gu[3],
-                                                        float gv[3]) {
+                                                        const float g[3], int tap[4], float tw[4],
+                                                        int &cell, float gz[3], float gu[3], float gv[3]) {
     const TexCoord tc = texel_coord(q, z, u, v, eps);
     const float depth = tc.depth, nx = tc.nx, ny = tc.ny, x0 = tc.x0, y0 = tc.y0, xf = tc.xf, yf = tc.yf;
     const float *zz = tc.zz;
@@ -99,24 +98,22 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
     const float xff = floorf(xf), yff = floorf(yf), xcf = xff + 1.f, ycf = yff + 1.f;
     const int xfi = (int)xff, yfi = (int)yff, xci = (int)xcf, yci = (int)ycf;
     const float ax = xcf - xf, bx = xf - xff, ay = ycf - yf, by = yf - yff;
-    const float w1 = ay * ax, w2 = ay * bx, w3 = by * ax, w4 = by * bx;
+    tw[0] = ay * ax; tw[1] = ay * bx; tw[2] = by * ax; tw[3] = by * bx;
     const int T = H * W;
-    const int i1 = yfi * W + xfi, i2 = yfi * W + xci, i3 = yci * W + xfi, i4 = yci * W + xci;
-    const bool ok1 = (unsigned)i1 < (unsigned)T, ok2 = (unsigned)i2 < (unsigned)T;
-    const bool ok3 = (unsigned)i3 < (unsigned)T, ok4 = (unsigned)i4 < (unsigned)T;
-    float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+    tap[0] = yfi * W + xfi; tap[1] = yfi * W + xci; tap[2] = yci * W + xfi; tap[3] = yci * W + xci;
+    cell = (yfi << 16) ^ (xfi & 0xffff);   // identifies the bilinear cell: equal cell => equal four taps
+    float d[4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float *p = tex_b + (size_t)c * T;
-        float *gp = gtex_b ? gtex_b + (size_t)c * T : nullptr;
-        const float gc = g[c];
-        if (ok1) { d1 += gc * __ldg(p + i1); if (gp && gc != 0.f) atomicAdd(gp + i1, w1 * gc); }
-        if (ok2) { d2 += gc * __ldg(p + i2); if (gp && gc != 0.f) atomicAdd(gp + i2, w2 * gc); }
-        if (ok3) { d3 += gc * __ldg(p + i3); if (gp && gc != 0.f) atomicAdd(gp + i3, w3 * gc); }
-        if (ok4) { d4 += gc * __ldg(p + i4); if (gp && gc != 0.f) atomicAdd(gp + i4, w4 * gc); }
+    for (int t = 0; t < 4; ++t) {
+        if ((unsigned)tap[t] >= (unsigned)T) tap[t] = -1;
+        d[t] = 0.f;
+        if (tap[t] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[t] += g[c] * __ldg(tex_b + (size_t)c * T + tap[t]);
+        }
     }
-    const float gxf = ay * (d2 - d1) + by * (d4 - d3);
-    const float gyf = ax * (d3 - d1) + bx * (d4 - d2);
+    const float gxf = ay * (d[1] - d[0]) + by * (d[3] - d[2]);
+    const float gyf = ax * (d[2] - d[0]) + bx * (d[3] - d[1]);
     float sx, sxlo, sxhi, sy, sylo, syhi;
     clamp_shares(x0, ulo, uhi, sx, sxlo, sxhi);
     clamp_shares(y0, vlo, vhi, sy, sylo, syhi);
@@ -138,110 +135,231 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
     gv[first_argmax3(v)] += gyf * syhi;
 }
 
+// Warp-level segmented sum over runs of equal `key` in lane order (a warp is one image row
+// segment, so the pixels of one face / one texel cell form runs).  Afterwards the LAST lane of
+// every run holds the run total in v[]; returns true on those lanes.  Fixed summation order.
+// Lanes with valid == false never join a run.
+template <int N>
+__device__ __forceinline__ bool run_reduce(int key, bool valid, float (&v)[N], int lane) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool prev_valid = __shfl_up_sync(0xffffffffu, (int)valid, 1) != 0;
+    // an invalid lane is a run of its own and separates the runs around it
+    const bool head = (lane == 0) || !valid || !prev_valid || (key != prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (heads != 0xffffffffu) {
+        const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const bool take = (lane - d >= seg_start);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float t = __shfl_up_sync(0xffffffffu, v[i], d);
+                if (take) v[i] += t;
+            }
+        }
+    }
+    return (lane == 31) || ((heads >> (lane + 1)) & 1u);
+}
+
+// C = channel count at compile time (0: read it from the arguments).
+// Persistent over the forward's list of non-empty 16x16 tiles (grid-stride); a warp owns two
+// 16-pixel row segments of the tile, so the pixels of one face form runs in lane order.
+template <int CT>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_backward(const BackwardArgs a) {
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x, b = blockIdx.y;
-    const int tx = tile % a.ntx, ty = tile / a.ntx;
-    const int R = a.R, S = a.S, C = a.C;
-    int px, py;
-    tile_pixel(tid, px, py);
-    const int xi = tx * TILE + px, yi = ty * TILE + py;
-    if (xi >= R || yi >= R) return;
+    const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+    const int R = a.R, S = a.S, C = CT ? CT : a.C;
+    const int nt = a.ntx * a.ntx;
+    const int count = a.tile_list ? a.tile_list[0] : a.B * nt;
+    for (int work = blockIdx.x; work < count; work += gridDim.x) {
+    int b, tx, ty;
+    if (a.tile_list) {
+        const int4 e = __ldg(reinterpret_cast<const int4 *>(a.tile_list + TILE_LIST_HDR) + work);
+        b = e.x; tx = e.y & 0xffff; ty = e.y >> 16;
+    } else {
+        b = work / nt;
+        const int tile = work - b * nt;
+        ty = tile / a.ntx; tx = tile - ty * a.ntx;
+    }
+    const int xi = tx * TILE + (lane & 15), yi = ty * TILE + wrow * 2 + (lane >> 4);
+    const bool valid = (xi < R) && (yi < R);
+    const int f = valid ? __ldg(a.fim + ((size_t)b * R + yi) * R + xi) : -1;
+    const bool fg = f >= 0;
+    // gradients only reach the mesh through foreground pixels (to_map links nothing else,
+    // utils.py:104-114): a warp without any is done with this tile
+    if (__ballot_sync(0xffffffffu, fg) == 0u) continue;
+
     const int u_ = R - 1 - yi, v_ = R - 1 - xi;
     const bool aa = (a.flags & FLAG_AA) != 0;
-
-    const float *Ib = a.internal + (size_t)b * C * R * R;
-    const float *Gb = a.grad_images + (size_t)b * C * S * S;
-    auto LI = [&](int c, int dy, int dx) -> float {
-        return __ldg(Ib + ((size_t)c * R + (u_ - dy)) * R + (v_ - dx));
-    };
-    auto LG = [&](int c, int dy, int dx) -> float {
-        const int uu = u_ - dy, vv = v_ - dx;
-        return aa ? __fmul_rn(__ldg(Gb + ((size_t)c * S + (uu >> 1)) * S + (vv >> 1)), 0.25f)
-                  : __ldg(Gb + ((size_t)c * S + uu) * S + vv);
-    };
-    const float stepf = (float)(2. / R);
-    const float inv_step = __frcp_rn(stepf);
-    float gx, gy;
-    diff_stencil(yi, xi, R, C, inv_step, LI, LG, gx, gy);
-
-    const int f = a.fim[((size_t)b * R + yi) * R + xi];
-    if (f < 0) return;   // gradients only reach the mesh through foreground pixels
-
-    int vid[3];
-    if (a.faces) {
-        vid[0] = __ldg(a.faces + 3 * (size_t)f);
-        vid[1] = __ldg(a.faces + 3 * (size_t)f + 1);
-        vid[2] = __ldg(a.faces + 3 * (size_t)f + 2);
-    } else {
-        vid[0] = 3 * f; vid[1] = 3 * f + 1; vid[2] = 3 * f + 2;
-    }
-    const float *vb = a.verts + (size_t)b * a.nv * 3;
-    float X[3], Y[3], Z[3];
+    float gx = 0.f, gy = 0.f;
+    float gcen[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // upstream gradient at this pixel, per channel
+    if (fg) {
+        // neighbour coordinates, clamped so every load is in range; out-of-range pairs are masked
+        const bool has_yp = yi + 1 < R, has_ym = yi > 0, has_xp = xi + 1 < R, has_xm = xi > 0;
+        const int u_yp = has_yp ? u_ - 1 : u_, u_ym = has_ym ? u_ + 1 : u_;
+        const int v_xp = has_xp ? v_ - 1 : v_, v_xm = has_xm ? v_ + 1 : v_;
+        const float *Ib = a.internal + (size_t)b * C * R * R;
+        const float *Gb = a.grad_images + (size_t)b * C * S * S;
+        const float gs = aa ? 0.25f : 1.f;   // 2x2 mean backward (rasterize.py:323-328), exact
+        const int sh = aa ? 1 : 0;
+        const size_t i_c = (size_t)u_ * R + v_, i_yp = (size_t)u_yp * R + v_, i_ym = (size_t)u_ym * R + v_;
+        const size_t i_xp = (size_t)u_ * R + v_xp, i_xm = (size_t)u_ * R + v_xm;
+        const size_t g_c = (size_t)(u_ >> sh) * S + (v_ >> sh), g_yp = (size_t)(u_yp >> sh) * S + (v_ >> sh);
+        const size_t g_ym = (size_t)(u_ym >> sh) * S + (v_ >> sh), g_xp = (size_t)(u_ >> sh) * S + (v_xp >> sh);
+        const size_t g_xm = (size_t)(u_ >> sh) * S + (v_xm >> sh);
+        float ry_i = 0.f, ry_m = 0.f, ly_m = 0.f, ly_i = 0.f, rx_i = 0.f, rx_m = 0.f, lx_m = 0.f, lx_i = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        X[k] = __ldg(vb + 3 * (size_t)vid[k]);
-        Y[k] = __ldg(vb + 3 * (size_t)vid[k] + 1);
-        Z[k] = __ldg(vb + 3 * (size_t)vid[k] + 2);
-    }
-    const float xp = pix_center(xi, R), yp = pix_center(yi, R);
-    float q[3];
-    raw_weights(xp, yp, X[0], Y[0], X[1], Y[1], X[2], Y[2], q[0], q[1], q[2]);
-    normalize_weights(q[0], q[1], q[2]);
-
-    float gz[3] = {0.f, 0.f, 0.f};
-    int c0 = 0;
-    if (a.flags & FLAG_RGB) {
-        const float g[3] = {LG(0, 0, 0), LG(1, 0, 0), LG(2, 0, 0)};
-        if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
-            const int32_t *fti = a.ft + 3 * (size_t)f;
-            const float *vtb = a.vt + (size_t)b * a.nvt * 2;
-            int tvid[3];
-            float u[3], v[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                tvid[k] = __ldg(fti + k);
-                const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + tvid[k]);
-                u[k] = uv.x;
-                v[k] = uv.y;
+        for (int c = 0; c < (CT ? CT : 5); ++c) {
+            if (c < C) {
+                const float *Ic = Ib + (size_t)c * R * R;
+                const float *Gc = Gb + (size_t)c * S * S;
+                const float ic = __ldg(Ic + i_c), iyp = __ldg(Ic + i_yp), iym = __ldg(Ic + i_ym);
+                const float ixp = __ldg(Ic + i_xp), ixm = __ldg(Ic + i_xm);
+                const float gc = __fmul_rn(__ldg(Gc + g_c), gs), gyp = __fmul_rn(__ldg(Gc + g_yp), gs);
+                const float gym = __fmul_rn(__ldg(Gc + g_ym), gs), gxp = __fmul_rn(__ldg(Gc + g_xp), gs);
+                const float gxm = __fmul_rn(__ldg(Gc + g_xm), gs);
+                gcen[c] = gc;
+                // differentiation.py:19-29; a clamped (out-of-range) neighbour equals the centre, so its
+                // difference is exactly zero and the term vanishes like the zero padding does
+                ry_i = __fadd_rn(ry_i, __fmul_rn(__fsub_rn(ic, iyp), gyp));
+                ly_i = __fadd_rn(ly_i, __fmul_rn(__fsub_rn(iyp, ic), gc));
+                ry_m = __fadd_rn(ry_m, __fmul_rn(__fsub_rn(iym, ic), gc));
+                ly_m = __fadd_rn(ly_m, __fmul_rn(__fsub_rn(ic, iym), gym));
+                rx_i = __fadd_rn(rx_i, __fmul_rn(__fsub_rn(ic, ixp), gxp));
+                lx_i = __fadd_rn(lx_i, __fmul_rn(__fsub_rn(ixp, ic), gc));
+                rx_m = __fadd_rn(rx_m, __fmul_rn(__fsub_rn(ixm, ic), gc));
+                lx_m = __fadd_rn(lx_m, __fmul_rn(__fsub_rn(ic, ixm), gxm));
             }
-            float gu[3], gv[3];
-            sample_texture_backward(a.tex + (size_t)b * 3 * a.H * a.W,
-                                    a.grad_tex ? a.grad_tex + (size_t)b * 3 * a.H * a.W : nullptr, a.H,
-                                    a.W, a.eps, q, Z, u, v, g, gz, gu, gv);
-            if (a.grad_vt) {
-                float *gvt = a.grad_vt + (size_t)b * a.nvt * 2;
+        }
+        const float inv_step = __frcp_rn((float)(2. / R));
+        const float gyr = __fadd_rn(__fmul_rn(-ry_i, inv_step), __fmul_rn(-ry_m, inv_step));
+        const float gyl = __fadd_rn(__fmul_rn(-ly_m, inv_step), __fmul_rn(-ly_i, inv_step));
+        const float gxr = __fadd_rn(__fmul_rn(-rx_i, inv_step), __fmul_rn(-rx_m, inv_step));
+        const float gxl = __fadd_rn(__fmul_rn(-lx_m, inv_step), __fmul_rn(-lx_i, inv_step));
+        gy = nr_maximum(gyr, gyl);
+        gx = nr_maximum(gxr, gxl);
+    }
+
+    // ---- per-pixel contributions
+    int vid[3] = {0, 0, 0};
+    float vg[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // (x, y, z) gradient of the 3 corners
+    float tg[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 4 taps x rgb
+    int tap[4] = {-1, -1, -1, -1};
+    int cell = 0;
+    bool has_tex = false;
+    const bool rgb = (a.flags & FLAG_RGB) != 0;
+    if (fg) {
+        if (a.faces) {
+            vid[0] = __ldg(a.faces + 3 * (size_t)f);
+            vid[1] = __ldg(a.faces + 3 * (size_t)f + 1);
+            vid[2] = __ldg(a.faces + 3 * (size_t)f + 2);
+        } else {
+            vid[0] = 3 * f; vid[1] = 3 * f + 1; vid[2] = 3 * f + 2;
+        }
+        const float *vb = a.verts + (size_t)b * a.nv * 3;
+        float X[3], Y[3], Z[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[k] = __ldg(vb + 3 * (size_t)vid[k]);
+            Y[k] = __ldg(vb + 3 * (size_t)vid[k] + 1);
+            Z[k] = __ldg(vb + 3 * (size_t)vid[k] + 2);
+        }
+        const float xp = pix_center(xi, R), yp = pix_center(yi, R);
+        float q[3];
+        raw_weights(xp, yp, X[0], Y[0], X[1], Y[1], X[2], Y[2], q[0], q[1], q[2]);
+        normalize_weights(q[0], q[1], q[2]);
+        float gz[3] = {0.f, 0.f, 0.f};
+        int c0 = 0;
+        if (rgb) {
+            const float g[3] = {gcen[0], gcen[1], gcen[2]};
+            if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
+                const int32_t *fti = a.ft + 3 * (size_t)f;
+                const float *vtb = a.vt + (size_t)b * a.nvt * 2;
+                int tvid[3];
+                float u[3], v[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    if (gu[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k], gu[k]);
-                    if (gv[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k] + 1, gv[k]);
+                    tvid[k] = __ldg(fti + k);
+                    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + tvid[k]);
+                    u[k] = uv.x;
+                    v[k] = uv.y;
+                }
+                float gu[3], gv[3], tw[4];
+                sample_texture_backward(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g,
+                                        tap, tw, cell, gz, gu, gv);
+                has_tex = true;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) tg[t * 3 + c] = tw[t] * g[c];
+                if (a.grad_vt) {
+                    float *gvt = a.grad_vt + (size_t)b * a.nvt * 2;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (gu[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k], gu[k]);
+                        if (gv[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k] + 1, gv[k]);
+                    }
+                }
+            }
+            c0 = 3;
+        }
+        if (a.flags & FLAG_SIL) ++c0;
+        if (a.flags & FLAG_DEPTH) {
+            const float gd = gcen[c0 < 5 ? c0 : 4];
+            if (gd != 0.f) {
+                const float s = (q[0] / Z[0] + q[1] / Z[1]) + q[2] / Z[2];
+                const float dm = 1.f / s;
+                const float t = gd * dm * dm;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) gz[k] += t * q[k] / (Z[k] * Z[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vg[3 * k] = q[k] * gx;
+            vg[3 * k + 1] = q[k] * gy;
+            vg[3 * k + 2] = gz[k];
+        }
+    }
+
+    // ---- vertices: one atomic per (run of equal face, corner, coordinate)
+    {
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nz |= (vg[i] != 0.f);
+        if (__ballot_sync(0xffffffffu, nz) != 0u) {
+            const bool tail = run_reduce<9>(f, fg, vg, lane);
+            if (tail && fg) {
+                float *gvb = a.grad_verts + (size_t)b * a.nv * 3;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    float *dst = gvb + 3 * (size_t)vid[k];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (vg[3 * k + c] != 0.f) atomicAdd(dst + c, vg[3 * k + c]);
                 }
             }
         }
-        c0 = 3;
     }
-    if (a.flags & FLAG_SIL) ++c0;
-    if (a.flags & FLAG_DEPTH) {
-        const float gd = LG(c0, 0, 0);
-        if (gd != 0.f) {
-            const float s = (q[0] / Z[0] + q[1] / Z[1]) + q[2] / Z[2];
-            const float dm = 1.f / s;
-            const float t = gd * dm * dm;
+    // ---- textures: one atomic per (run of equal base texel, tap, channel)
+    if (rgb && a.grad_tex) {
+        const bool has = has_tex;
+        if (__ballot_sync(0xffffffffu, has) != 0u) {
+            const bool tail = run_reduce<12>(cell, has, tg, lane);
+            if (tail && has) {
+                float *gtb = a.grad_tex + (size_t)b * 3 * a.H * a.W;
+                const size_t T = (size_t)a.H * a.W;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) gz[k] += t * q[k] / (Z[k] * Z[k]);
+                for (int t = 0; t < 4; ++t) {
+                    if (tap[t] < 0) continue;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (tg[t * 3 + c] != 0.f) atomicAdd(gtb + c * T + tap[t], tg[t * 3 + c]);
+                }
+            }
         }
     }
-
-    float *gvb = a.grad_verts + (size_t)b * a.nv * 3;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float *dst = gvb + 3 * (size_t)vid[k];
-        const float cx = q[k] * gx, cy = q[k] * gy;
-        if (cx != 0.f) atomicAdd(dst, cx);
-        if (cy != 0.f) atomicAdd(dst + 1, cy);
-        if (gz[k] != 0.f) atomicAdd(dst + 2, gz[k]);
-    }
+    }   // tiles
 }
 
 // Differentiation.backward on channels-last tensors (the public differentiation() op).
@@ -265,9 +383,16 @@ k_differentiation_backward(const float *__restrict__ images, const float *__rest
 
 cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
-    dim3 grid(a.ntx * a.ntx, a.B);
+    const long long tiles = (long long)a.ntx * a.ntx * a.B;
+    const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
+    dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
-    k_backward<<<grid, TILE_THREADS, 0, stream>>>(a);
+    switch (a.C) {
+        case 1: k_backward<1><<<grid, block, 0, stream>>>(a); break;
+        case 3: k_backward<3><<<grid, block, 0, stream>>>(a); break;
+        case 4: k_backward<4><<<grid, block, 0, stream>>>(a); break;
+        default: k_backward<0><<<grid, block, 0, stream>>>(a); break;
+    }
     return cudaGetLastError();
 }
 

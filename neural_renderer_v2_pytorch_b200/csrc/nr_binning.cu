@@ -12,8 +12,8 @@
 //                   counts the face into every 16x16 tile its pixel box touches.
 //   k_scan_tiles  : exclusive prefix sum of the per-tile counts (one CTA per view).
 //   k_scatter     : writes face ids into the tile segments (slot order is arbitrary ...)
-//   k_sort_long   : ... so segments are sorted: long ones here in global memory, short ones
-//                   in shared memory by the raster kernel itself.
+//   k_sort_tiles  : ... so every list is sorted in place (one warp per list, most are already
+//   k_sort_long     in order); lists longer than SMEM_SORT_CAP go through k_sort_long.
 #include "nr_kernels.h"
 
 namespace nr {
@@ -95,8 +95,8 @@ k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces
 // pair list is claimed with one atomicAdd (segment placement is arbitrary, content is not).
 __global__ void __launch_bounds__(1024)
 k_scan_tiles(const int *__restrict__ tile_count, int *__restrict__ tile_offset,
-             int *__restrict__ tile_cursor, int nt, long long pair_capacity,
-             BinHeader *__restrict__ hdr) {
+             int *__restrict__ tile_cursor, int nt, int ntx, long long pair_capacity,
+             BinHeader *__restrict__ hdr, int32_t *__restrict__ tile_list) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -153,6 +153,17 @@ k_scan_tiles(const int *__restrict__ tile_count, int *__restrict__ tile_offset,
             tile_offset[(size_t)b * nt + i] = excl;
             tile_cursor[(size_t)b * nt + i] = excl;
         }
+        // append the non-empty tiles to the work list (one atomic per warp)
+        const unsigned busy = __ballot_sync(0xffffffffu, v > 0);
+        if (busy) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&tile_list[0], __popc(busy));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (v > 0) {
+                int4 *ent = reinterpret_cast<int4 *>(tile_list + TILE_LIST_HDR) + base + __popc(busy & ((1u << lane) - 1u));
+                *ent = make_int4(b, (i % ntx) | ((i / ntx) << 16), excl, v);
+            }
+        }
         carry += s_warp[31];
         __syncthreads();
     }
@@ -179,8 +190,85 @@ k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restri
         }
 }
 
-// Ascending in-place sort of the segments that are too long for the raster kernel's
-// shared-memory sort.  Same-direction bitonic network over a virtual power-of-two length
+// Ascending in-place sort of every tile list of up to SMEM_SORT_CAP faces: one warp per tile,
+// grid-stride over the work list.  The scatter kernel mostly claims slots in face order already, so
+// most lists only pay the sortedness check.  Lists of <= 32 ids are rank-sorted in registers,
+// longer ones with a same-direction bitonic network in this warp's slice of shared memory.
+constexpr int SORT_WARPS = 4;
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
+             const BinHeader *__restrict__ hdr) {
+    __shared__ int s_ids[SORT_WARPS][SMEM_SORT_CAP];
+    if (hdr->overflow) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = tile_list[0];
+    const int4 *entries = reinterpret_cast<const int4 *>(tile_list + TILE_LIST_HDR);
+    for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
+        const int4 e = entries[w];
+        const int n = e.w;
+        if (n < 2 || n > SMEM_SORT_CAP) continue;
+        int32_t *a = pairs + e.z;
+        if (n <= 32) {
+            const int v = lane < n ? a[lane] : 0x7fffffff;
+            const int nxt = __shfl_down_sync(0xffffffffu, v, 1);
+            if (__ballot_sync(0xffffffffu, lane < 31 && v > nxt) == 0u) continue;
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rank += (__shfl_sync(0xffffffffu, v, j) < v);
+            if (lane < n) a[rank] = v;     // ids are unique inside one list
+            continue;
+        }
+        int *sm = s_ids[wid];
+        int unsorted = 0;
+        for (int i = lane; i < n; i += 32) sm[i] = a[i];
+        __syncwarp();
+        for (int i = lane; i + 1 < n; i += 32) unsorted |= (sm[i] > sm[i + 1]);
+        if (__ballot_sync(0xffffffffu, unsorted) == 0u) continue;
+        if (n <= 64) {
+            // rank sort straight from the shared copy into global memory
+            for (int i = lane; i < n; i += 32) {
+                const int v = sm[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) rank += (sm[j] < v);
+                a[rank] = v;
+            }
+            __syncwarp();
+            continue;
+        }
+        int lg = 6;
+        while ((1 << lg) < n) ++lg;
+        const int half = 1 << (lg - 1);
+        for (int kk = 1; kk <= lg; ++kk) {
+            const int k = 1 << kk;
+            for (int i = lane; i < half; i += 32) {
+                const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
+                const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
+                if (hi < n && sm[lo] > sm[hi]) {
+                    const int t = sm[lo];
+                    sm[lo] = sm[hi];
+                    sm[hi] = t;
+                }
+            }
+            __syncwarp();
+            for (int jj = kk - 2; jj >= 0; --jj) {
+                const int j = 1 << jj;
+                for (int i = lane; i < half; i += 32) {
+                    const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
+                    if (hi < n && sm[lo] > sm[hi]) {
+                        const int t = sm[lo];
+                        sm[lo] = sm[hi];
+                        sm[hi] = t;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < n; i += 32) a[i] = sm[i];
+        __syncwarp();
+    }
+}
+
+// Ascending in-place sort of the segments that are too long for the shared-memory sort.  Same-direction bitonic network over a virtual power-of-two length
 // (indices >= n behave as +inf and never move), one CTA per long segment, grid-stride over tiles.
 __global__ void __launch_bounds__(256)
 k_sort_long(const int *__restrict__ tile_count, const int *__restrict__ tile_offset, int total_tiles,
@@ -230,6 +318,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
     {
         ProfScope p(PROF_MEMSET, stream);
         e = cudaMemsetAsync(a.hdr, 0, sizeof(BinHeader) + sizeof(int) * (size_t)a.B * nt, stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(a.tile_list, 0, sizeof(int32_t) * TILE_LIST_HDR, stream);
     }
     if (e != cudaSuccess) return e;
     const long long nface = (long long)a.B * a.nf;
@@ -241,8 +330,8 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
     }
     {
         ProfScope p(PROF_SCAN, stream);
-        k_scan_tiles<<<a.B, 1024, 0, stream>>>(a.tile_count, a.tile_offset, a.tile_cursor, nt,
-                                               a.pair_capacity, a.hdr);
+        k_scan_tiles<<<a.B, 1024, 0, stream>>>(a.tile_count, a.tile_offset, a.tile_cursor, nt, a.ntx,
+                                               a.pair_capacity, a.hdr, a.tile_list);
     }
     if (nface > 0) {
         const unsigned blocks = (unsigned)((nface + 255) / 256);
@@ -252,6 +341,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
                                                   a.pair_capacity, a.hdr);
         }
         ProfScope p(PROF_SORT_LONG, stream);
+        k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.pairs, a.hdr);
         k_sort_long<<<a.sm_count * 2, 256, 0, stream>>>(a.tile_count, a.tile_offset, a.B * nt, a.pairs,
                                                         SMEM_SORT_CAP, a.hdr);
     }

@@ -26,8 +26,15 @@ struct BinHeader {
     int max_tile_faces;
     int overflow;
     int bad_index;
-    int pad[60];
+    int work_counter;   // dynamic tile scheduler of the persistent raster kernel
+    int pad[59];
 };
+
+// Non-empty tiles of one forward call, consumed by the raster kernel and again by the backward:
+//   list[0] = number of entries; entry i = 4 ints at list[TILE_LIST_HDR + 4 i]:
+//   (view, tile_x | tile_y << 16, offset of the tile's face list in the pair array, its length)
+constexpr int TILE_LIST_HDR = 4;
+constexpr int TILE_ENTRY_INTS = 4;
 static_assert(sizeof(BinHeader) == 256, "header is one 256-byte block");
 
 // Per (view, face) record written by the setup kernel: 48 bytes, three float4 loads.

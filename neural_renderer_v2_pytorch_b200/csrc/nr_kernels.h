@@ -30,6 +30,7 @@ struct BinningArgs {
     int32_t *pairs;
     long long pair_capacity;
     BinHeader *hdr;
+    int32_t *tile_list;     // [TILE_LIST_HDR + B * ntx * ntx], zeroed here
     int sm_count;
 };
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
@@ -38,7 +39,9 @@ struct RasterArgs {
     const FaceRec *rec;
     const int *tile_count, *tile_offset;
     const int32_t *pairs;
-    const BinHeader *hdr;
+    BinHeader *hdr;
+    const int32_t *tile_list;
+    int sm_count;
     int B, nf, R, S, ntx, C, flags;
     float near_plane, far_plane, eps, delta;
     const float *vt;        // [B, nvt, 2]
@@ -62,6 +65,8 @@ struct BackwardArgs {
     const int32_t *fim;
     const float *internal;  // [B, C, R, R] flipped planar
     const float *grad_images;   // [B, C, S, S]
+    const int32_t *tile_list;   // non-empty tiles of the forward, or null (all tiles)
+    int sm_count;
     float *grad_verts, *grad_tex, *grad_vt;
     int B, nv, nf, R, S, ntx, C, flags, nvt, H, W;
     float eps;

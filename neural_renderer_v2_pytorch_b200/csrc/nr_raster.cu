@@ -13,58 +13,6 @@
 
 namespace nr {
 
-// Ascending sort of a[0..n) in shared memory, n <= SMEM_SORT_CAP. Face ids inside one tile list
-// are unique.  Already-sorted lists (the common case: the scatter kernel mostly claims slots in
-// face order) only pay the check.
-__device__ void sort_ids_smem(int *a, int *scratch, int n) {
-    const int tid = threadIdx.x;
-    int unsorted = 0;
-    for (int i = tid; i + 1 < n; i += TILE_THREADS) unsorted |= (a[i] > a[i + 1]);
-    if (!__syncthreads_or(unsorted)) return;
-    if (n <= TILE_THREADS) {
-        // rank sort: position = number of smaller ids
-        int v = 0, rank = 0;
-        if (tid < n) {
-            v = a[tid];
-            for (int j = 0; j < n; ++j) rank += (a[j] < v);
-        }
-        __syncthreads();
-        if (tid < n) a[rank] = v;
-        __syncthreads();
-        return;
-    }
-    (void)scratch;
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int i = tid; i < np2 / 2; i += TILE_THREADS) {
-            const int blk = i / (k / 2), off = i % (k / 2);
-            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
-            if (hi < n) {
-                const int x = a[lo], y = a[hi];
-                if (x > y) {
-                    a[lo] = y;
-                    a[hi] = x;
-                }
-            }
-        }
-        __syncthreads();
-        for (int j = k / 4; j >= 1; j >>= 1) {
-            for (int i = tid; i < np2 / 2; i += TILE_THREADS) {
-                const int lo = (i / j) * 2 * j + (i % j), hi = lo + j;
-                if (hi < n) {
-                    const int x = a[lo], y = a[hi];
-                    if (x > y) {
-                        a[lo] = y;
-                        a[hi] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // Perspective-correct bilinear texture sample of one foreground pixel, rasterize.py:100-153.
 // q = weight map, z = face depths, uv = texel coordinates of the 3 face corners.
 __device__ __forceinline__ void sample_texture(const float *__restrict__ tex_b, int H, int W,
@@ -95,80 +43,147 @@ __device__ __forceinline__ void sample_texture(const float *__restrict__ tex_b, 
     }
 }
 
+// Conservative test "no pixel of the block [xa, xb] x [ya, yb] (pixel-centre coordinates) can pass
+// the reference's inside test for this face" (rasterize_cuda_kernel.cu:107-116).  The reference accepts
+// a pixel iff c1*c2 >= 0 and c2*c3 >= 0 in float arithmetic, which also lets every pixel with c2 == 0
+// (or an underflowing product) through.  So a block is only rejected when, over the whole block, c2
+// is bounded away from zero AND c1 or c3 is bounded away from zero with the opposite sign.  The edge
+// functions are affine, so their range over the block is spanned by the four corners; the bounds
+// carry a margin 40x above the rounding error of the reference's float evaluation.  NaN never rejects.
+__device__ __forceinline__ bool block_outside_face(float x0, float y0, float x1, float y1, float x2,
+                                                   float y2, float xa, float xb, float ya, float yb) {
+    const float dx10 = x1 - x0, dy10 = y1 - y0, dx21 = x2 - x1, dy21 = y2 - y1, dx02 = x0 - x2, dy02 = y0 - y2;
+    float lo1, hi1, lo2, hi2, lo3, hi3;
+    {
+        const float a = (ya - y0) * dx10, b = (yb - y0) * dx10, c = dy10 * (xa - x0), d = dy10 * (xb - x0);
+        lo1 = fminf(a, b) - fmaxf(c, d);
+        hi1 = fmaxf(a, b) - fminf(c, d);
+        const float m = 1e-5f * (fmaxf(fabsf(a), fabsf(b)) + fmaxf(fabsf(c), fabsf(d))) + 1e-30f;
+        lo1 -= m;
+        hi1 += m;
+    }
+    {
+        const float a = (ya - y1) * dx21, b = (yb - y1) * dx21, c = dy21 * (xa - x1), d = dy21 * (xb - x1);
+        lo2 = fminf(a, b) - fmaxf(c, d);
+        hi2 = fmaxf(a, b) - fminf(c, d);
+        const float m = 1e-5f * (fmaxf(fabsf(a), fabsf(b)) + fmaxf(fabsf(c), fabsf(d))) + 1e-30f;
+        lo2 -= m;
+        hi2 += m;
+    }
+    {
+        const float a = (ya - y2) * dx02, b = (yb - y2) * dx02, c = dy02 * (xa - x2), d = dy02 * (xb - x2);
+        lo3 = fminf(a, b) - fmaxf(c, d);
+        hi3 = fmaxf(a, b) - fminf(c, d);
+        const float m = 1e-5f * (fmaxf(fabsf(a), fabsf(b)) + fmaxf(fabsf(c), fabsf(d))) + 1e-30f;
+        lo3 -= m;
+        hi3 += m;
+    }
+    const bool c2pos = lo2 > 0.f, c2neg = hi2 < 0.f;
+    return (c2pos && (hi1 < 0.f || hi3 < 0.f)) || (c2neg && (lo1 > 0.f || lo3 > 0.f));
+}
+
+// Persistent kernel over the non-empty tiles.  The unit of work is one WARP = one 8x4 pixel block
+// of a tile (warp-granular static grid-stride; the 8 warps of a CTA take the 8 blocks of one tile, so
+// the tile's records are shared through L1).  Warps never wait for each other: a block without
+// candidate faces costs one cull pass.  Per 32 faces of the tile list: every lane loads one face
+// record, tests its pixel box against the block, the survivors are compacted (ballot) into this
+// warp's slice of shared memory with their edge deltas, then evaluated per pixel in list order.
+// Background pixels were pre-filled by launch_raster, so only foreground pixels are written.
+constexpr int RASTER_WARPS = TILE_THREADS / 32;
+
 __global__ void __launch_bounds__(TILE_THREADS)
 k_raster(const RasterArgs a) {
-    __shared__ int s_ids[SMEM_SORT_CAP];
-    __shared__ float4 s_rec[TILE_THREADS][4];
-    __shared__ uint2 s_bb[TILE_THREADS];
+    __shared__ float4 s_rec[RASTER_WARPS][32][4];
+    __shared__ uint2 s_bb[RASTER_WARPS][32];
 
     if (a.hdr->overflow) return;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int tile = blockIdx.x, b = blockIdx.y;
-    const int tx = tile % a.ntx, ty = tile / a.ntx;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int R = a.R;
-    int px, py;
-    tile_pixel(tid, px, py);
-    const int xi = tx * TILE + px, yi = ty * TILE + py;
-    const bool valid = (xi < R) && (yi < R);
-    const float xp = pix_center(xi, R), yp = pix_center(yi, R);
-    // pixel block owned by this warp, for the warp-level cull
-    const int wx0 = tx * TILE + ((tid >> 5) & 1) * WARP_BW, wx1 = wx0 + WARP_BW - 1;
-    const int wy0 = ty * TILE + (tid >> 6) * WARP_BH, wy1 = wy0 + WARP_BH - 1;
+    const int count = a.tile_list[0];
+    const int4 *entries = reinterpret_cast<const int4 *>(a.tile_list + TILE_LIST_HDR);
+    const int items = count * RASTER_WARPS;
+    const bool aa = (a.flags & FLAG_AA) != 0;
+    const bool pow2 = (R & (R - 1)) == 0;
+    const float invR = 1.f / (float)R;          // exact for power-of-two R
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float4 (*my_rec)[4] = s_rec[wid];
+    uint2 *my_bb = s_bb[wid];
 
-    const int tflat = b * a.ntx * a.ntx + tile;
-    const int n = a.tile_count[tflat];
-    const int32_t *list = a.pairs + a.tile_offset[tflat];
-    const bool in_smem = (n <= SMEM_SORT_CAP);
-    if (in_smem && n > 0) {
-        for (int i = tid; i < n; i += TILE_THREADS) s_ids[i] = list[i];
-        __syncthreads();
-        sort_ids_smem(s_ids, nullptr, n);
-    }
+    // dynamic scheduling: a warp claims two adjacent blocks at a time; the next claim is issued
+    // before the current pair is processed so its latency is hidden
+    constexpr int GRAB = 2;
+    int claim = 0;
+    if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
+    while (true) {
+        const int first = __shfl_sync(0xffffffffu, claim, 0);
+        if (first >= items) break;
+        if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
+    for (int item = first; item < min(first + GRAB, items); ++item) {
+        const int4 e0 = __ldg(entries + (item >> 3));
+        const int sub = item & 7;
+        const int b = e0.x, n = e0.w;
+        const int32_t *list = a.pairs + e0.z;
+        const int wx0 = (e0.y & 0xffff) * TILE + (sub & 1) * WARP_BW, wx1 = wx0 + WARP_BW - 1;
+        const int wy0 = (e0.y >> 16) * TILE + (sub >> 1) * WARP_BH, wy1 = wy0 + WARP_BH - 1;
+        const int xi = wx0 + (lane & 7), yi = wy0 + (lane >> 3);
+        const bool valid = (xi < R) && (yi < R);
+        const float xp = pow2 ? __fmul_rn((float)(2 * xi + 1 - R), invR) : pix_center(xi, R);
+        const float yp = pow2 ? __fmul_rn((float)(2 * yi + 1 - R), invR) : pix_center(yi, R);
+        const FaceRec *rec_b = a.rec + (size_t)b * a.nf;
+        // pixel centres of the block's corner pixels, for the conservative edge cull
+        const float xa = pow2 ? __fmul_rn((float)(2 * wx0 + 1 - R), invR) : pix_center(wx0, R);
+        const float xb = pow2 ? __fmul_rn((float)(2 * wx1 + 1 - R), invR) : pix_center(wx1, R);
+        const float ya = pow2 ? __fmul_rn((float)(2 * wy0 + 1 - R), invR) : pix_center(wy0, R);
+        const float yb = pow2 ? __fmul_rn((float)(2 * wy1 + 1 - R), invR) : pix_center(wy1, R);
 
-    float depth_min = a.far_plane;
-    int best = -1;
-    float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
-    const FaceRec *rec_b = a.rec + (size_t)b * a.nf;
+        float depth_min = a.far_plane;
+        int best = -1;
+        float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
 
-    for (int c0 = 0; c0 < n; c0 += TILE_THREADS) {
-        const int cn = min(TILE_THREADS, n - c0);
-        if (tid < cn) {
-            const int fid = in_smem ? s_ids[c0 + tid] : list[c0 + tid];
-            const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid);
-            const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
-            const float x0 = q0.x, y0 = q0.y, z0 = q0.z, x1 = q0.w;
-            const float y1 = q1.x, z1 = q1.y, x2 = q1.z, y2 = q1.w, z2 = q2.x;
-            s_rec[tid][0] = make_float4(x0, y0, x1, y1);
-            s_rec[tid][1] = make_float4(x2, y2, __fsub_rn(x1, x0), __fsub_rn(y1, y0));
-            s_rec[tid][2] = make_float4(__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(x0, x2), __fsub_rn(y0, y2));
-            s_rec[tid][3] = make_float4(z0, z1, z2, __int_as_float(fid));
-            s_bb[tid] = make_uint2(__float_as_uint(q2.y), __float_as_uint(q2.z));
-        }
-        __syncthreads();
-        for (int g = 0; g < cn; g += 32) {
+        for (int g = 0; g < n; g += 32) {
+            // ---- one face per lane: load, cull against this warp's block, compact the survivors
             bool hit = false;
-            if (g + lane < cn) {
-                const uint2 bb = s_bb[g + lane];
-                const int xlo = bb.x & 0xffff, xhi = bb.x >> 16, ylo = bb.y & 0xffff, yhi = bb.y >> 16;
-                hit = (xlo <= wx1) && (xhi >= wx0) && (ylo <= wy1) && (yhi >= wy0);
+            int fid = -1;
+            float4 q0, q1, q2;
+            if (g + lane < n) {
+                fid = __ldg(list + g + lane);
+                const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid);
+                q0 = __ldg(rp);
+                q1 = __ldg(rp + 1);
+                q2 = __ldg(rp + 2);
+                const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+                hit = ((int)(bx & 0xffff) <= wx1) && ((int)(bx >> 16) >= wx0) && ((int)(by & 0xffff) <= wy1) &&
+                      ((int)(by >> 16) >= wy0);
+                if (hit) hit = !block_outside_face(q0.x, q0.y, q0.w, q1.x, q1.z, q1.w, xa, xb, ya, yb);
             }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int j = g + __ffs(m) - 1;
-                m &= m - 1;
-                const uint2 bb = s_bb[j];
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            if (hit) {
+                const int slot = __popc(m & lt_mask);      // keeps list order
+                const float x0 = q0.x, y0 = q0.y, z0 = q0.z, x1 = q0.w;
+                const float y1 = q1.x, z1 = q1.y, x2 = q1.z, y2 = q1.w, z2 = q2.x;
+                my_rec[slot][0] = make_float4(x0, y0, x1, y1);
+                my_rec[slot][1] = make_float4(x2, y2, __fsub_rn(x1, x0), __fsub_rn(y1, y0));
+                my_rec[slot][2] = make_float4(__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(x0, x2), __fsub_rn(y0, y2));
+                my_rec[slot][3] = make_float4(z0, z1, z2, __int_as_float(fid));
+                my_bb[slot] = make_uint2(__float_as_uint(q2.y), __float_as_uint(q2.z));
+            }
+            __syncwarp();
+            const int nh = __popc(m);
+            for (int j = 0; j < nh; ++j) {
+                const uint2 bb = my_bb[j];
                 // :94-97, exact by construction of the pixel box
                 if (xi < (int)(bb.x & 0xffff) || xi > (int)(bb.x >> 16) || yi < (int)(bb.y & 0xffff) ||
                     yi > (int)(bb.y >> 16))
                     continue;
-                const float4 A = s_rec[j][0], Bq = s_rec[j][1], Cq = s_rec[j][2];
+                const float4 A = my_rec[j][0], Bq = my_rec[j][1], Cq = my_rec[j][2];
                 // :107-116
                 const float c1 = __fmaf_rn(__fsub_rn(yp, A.y), Bq.z, -__fmul_rn(Bq.w, __fsub_rn(xp, A.x)));
                 const float c2 = __fmaf_rn(__fsub_rn(yp, A.w), Cq.x, -__fmul_rn(Cq.y, __fsub_rn(xp, A.z)));
                 if (__fmul_rn(c1, c2) < 0.f) continue;
                 const float c3 = __fmaf_rn(__fsub_rn(yp, Bq.y), Cq.z, -__fmul_rn(Cq.w, __fsub_rn(xp, Bq.x)));
                 if (__fmul_rn(c2, c3) < 0.f) continue;
-                const float4 D = s_rec[j][3];
+                const float4 D = my_rec[j][3];
                 // :124-126
                 if (depth_min < D.x && depth_min < D.y && depth_min < D.z) continue;
                 // :129-136
@@ -188,78 +203,81 @@ k_raster(const RasterArgs a) {
                     bz0 = D.x; bz1 = D.y; bz2 = D.z;
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
-    }
+        if (__ballot_sync(0xffffffffu, best >= 0) == 0u) continue;   // nothing but background in this block
 
-    // ------------------------------------------------------------------ epilogue
-    const bool fg = best >= 0;
-    float q[3] = {0.f, 0.f, 0.f};
-    if (fg) {
-        q[0] = bw0; q[1] = bw1; q[2] = bw2;
-        normalize_weights(q[0], q[1], q[2]);
-    }
-    const size_t pix = ((size_t)b * R + yi) * R + xi;
-    if (valid) {
-        a.fim[pix] = best;
-        if (a.wmap) {
-            float *w = a.wmap + pix * 3;
-            w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
-        }
-    }
-    float dm = 0.f;
-    if (fg && ((a.flags & FLAG_DEPTH) || a.dmap))
-        dm = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fdiv_rn(q[0], bz0), __fdiv_rn(q[1], bz1)), __fdiv_rn(q[2], bz2)));
-    if (valid && a.dmap) a.dmap[pix] = dm;
-    if (!a.images) return;
-
-    float ch[5];
-    int C = 0;
-    if (a.flags & FLAG_RGB) {
-        float rgb[3] = {0.f, 0.f, 0.f};
+        // -------------------------------------------------------------- epilogue (foreground only)
+        const bool fg = valid && best >= 0;
+        float q[3] = {0.f, 0.f, 0.f};
         if (fg) {
-            const int32_t *fti = a.ft + 3 * (size_t)best;
-            const float *vtb = a.vt + (size_t)b * a.nvt * 2;
-            float u[3], v[3];
+            q[0] = bw0; q[1] = bw1; q[2] = bw2;
+            normalize_weights(q[0], q[1], q[2]);
+        }
+        const size_t pix = ((size_t)b * R + yi) * R + xi;
+        float dm = 0.f;
+        if (fg) {
+            a.fim[pix] = best;
+            if (a.wmap) {
+                float *w = a.wmap + pix * 3;
+                w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
+            }
+            if ((a.flags & FLAG_DEPTH) || a.dmap)
+                dm = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fdiv_rn(q[0], bz0), __fdiv_rn(q[1], bz1)), __fdiv_rn(q[2], bz2)));
+            if (a.dmap) a.dmap[pix] = dm;
+        }
+        if (a.images) {
+            const int C = a.C, S = a.S;
+            const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
+            const bool any_fg_quad = aa && __any_sync(0xffffffffu, fg);
+            // one channel value of this pixel -> images (and the internal-resolution copy under AA)
+            auto put = [&](int c, float val) {
+                if (!aa) {
+                    if (fg) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
+                    return;
+                }
+                if (!any_fg_quad) return;   // warp-uniform
+                if (fg) a.internal[(((size_t)b * C + c) * R + u_) * R + v_] = val;
+                // quad in flipped coordinates: F[2Y][2X] is (yi odd, xi odd); rasterize.py:323-328
+                const float px_ = __shfl_xor_sync(0xffffffffu, val, 1);   // same row, other column
+                const float py_ = __shfl_xor_sync(0xffffffffu, val, 8);   // other row, same column
+                const float pd_ = __shfl_xor_sync(0xffffffffu, val, 9);
+                const bool quad_fg = (__shfl_xor_sync(0xffffffffu, (int)fg, 1) | __shfl_xor_sync(0xffffffffu, (int)fg, 8) |
+                                      __shfl_xor_sync(0xffffffffu, (int)fg, 9) | (int)fg) != 0;
+                if (valid && quad_fg && !(xi & 1) && !(yi & 1)) {
+                    // me = (even, even) -> F[2Y+1][2X+1]; py_ = (odd row, even col) -> F[2Y][2X+1]
+                    // px_ = (even row, odd col) -> F[2Y+1][2X]; pd_ = (odd, odd) -> F[2Y][2X]
+                    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(pd_, px_), py_), val);
+                    a.images[(((size_t)b * C + c) * S + (u_ >> 1)) * S + (v_ >> 1)] = __fmul_rn(sum, 0.25f);
+                }
+            };
+            int c = 0;
+            if (a.flags & FLAG_RGB) {
+                float rgb[3] = {0.f, 0.f, 0.f};
+                if (fg) {
+                    const int32_t *fti = a.ft + 3 * (size_t)best;
+                    const float *vtb = a.vt + (size_t)b * a.nvt * 2;
+                    float u[3], v[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int t = __ldg(fti + k);
-                const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + t);
-                u[k] = uv.x;
-                v[k] = uv.y;
+                    for (int k = 0; k < 3; ++k) {
+                        const int t = __ldg(fti + k);
+                        const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + t);
+                        u[k] = uv.x;
+                        v[k] = uv.y;
+                    }
+                    const float z[3] = {bz0, bz1, bz2};
+                    sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
+                }
+                put(0, rgb[0]);
+                put(1, rgb[1]);
+                put(2, rgb[2]);
+                c = 3;
             }
-            const float z[3] = {bz0, bz1, bz2};
-            sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
+            if (a.flags & FLAG_SIL) put(c++, fg ? 1.f : 0.f);
+            if (a.flags & FLAG_DEPTH) put(c++, dm);
         }
-        ch[0] = rgb[0]; ch[1] = rgb[1]; ch[2] = rgb[2];
-        C = 3;
-    }
-    if (a.flags & FLAG_SIL) ch[C++] = fg ? 1.f : 0.f;
-    if (a.flags & FLAG_DEPTH) ch[C++] = dm;
-
-    const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
-    if (!(a.flags & FLAG_AA)) {
-        if (valid) {
-            for (int c = 0; c < C; ++c) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = ch[c];
-        }
-    } else {
-        const int S = a.S;
-        const bool writer = valid && !(xi & 1) && !(yi & 1);
-        for (int c = 0; c < C; ++c) {
-            const float me = ch[c];
-            if (valid && a.internal) a.internal[(((size_t)b * C + c) * R + u_) * R + v_] = me;
-            // quad in flipped coordinates: F[2Y][2X] is (yi odd, xi odd); rasterize.py:323-328
-            const float px_ = __shfl_xor_sync(0xffffffffu, me, 1);   // same row, other column
-            const float py_ = __shfl_xor_sync(0xffffffffu, me, 8);   // other row, same column
-            const float pd_ = __shfl_xor_sync(0xffffffffu, me, 9);
-            if (writer) {
-                // me = (even, even) -> F[2Y+1][2X+1]; py_ = (odd row, even col) -> F[2Y][2X+1]
-                // px_ = (even row, odd col) -> F[2Y+1][2X]; pd_ = (odd, odd) -> F[2Y][2X]
-                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(pd_, px_), py_), me);
-                a.images[(((size_t)b * C + c) * S + (u_ >> 1)) * S + (v_ >> 1)] = __fmul_rn(sum, 0.25f);
-            }
-        }
-    }
+    }   // items of this claim
+    }   // claims
 }
 
 // compute_weight_map_c compatibility kernel (rasterize_cuda_kernel.cu:246-308): one thread per
@@ -286,7 +304,20 @@ k_weight_map_compat(const float *__restrict__ faces, const int32_t *__restrict__
 
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
-    dim3 grid(a.ntx * a.ntx, a.B);
+    // background everywhere first; the kernel then writes foreground pixels only
+    {
+        ProfScope p(PROF_MEMSET, stream);
+        const size_t P = (size_t)a.B * a.R * a.R;
+        cudaError_t e = cudaMemsetAsync(a.fim, 0xff, P * sizeof(int32_t), stream);   // -1
+        if (e == cudaSuccess && a.wmap) e = cudaMemsetAsync(a.wmap, 0, P * 3 * sizeof(float), stream);
+        if (e == cudaSuccess && a.dmap) e = cudaMemsetAsync(a.dmap, 0, P * sizeof(float), stream);
+        if (e == cudaSuccess && a.images)
+            e = cudaMemsetAsync(a.images, 0, (size_t)a.B * a.C * a.S * a.S * sizeof(float), stream);
+        if (e == cudaSuccess && a.images && a.internal) e = cudaMemsetAsync(a.internal, 0, P * a.C * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const long long tiles = (long long)a.ntx * a.ntx * a.B;
+    const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
     ProfScope p(PROF_RASTER, stream);
     k_raster<<<grid, TILE_THREADS, 0, stream>>>(a);
     return cudaGetLastError();

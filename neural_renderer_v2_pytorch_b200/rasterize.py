@@ -89,7 +89,7 @@ def _flags_of(hp):
 
 def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
     """Runs nr_rasterize_forward, regrowing the pair list if it overflowed.
-    Returns (images, internal, fim, wmap, dmap)."""
+    Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
     dev = vertices.device
     B, S = cfg.batch, cfg.image_size
@@ -104,6 +104,8 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
         wmap = torch.empty((B, R, R, 3), dtype=torch.float32, device=dev) if want_maps else None
         dmap = torch.empty((B, R, R), dtype=torch.float32, device=dev) if want_maps else None
+        ntx = (R + 15) // 16
+        tile_list = torch.empty(4 + 4 * B * ntx * ntx, dtype=torch.int32, device=dev)
         capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
         for _ in range(4):
             sc.ensure(cfg, capacity)
@@ -112,7 +114,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
             aligned = (base + 255) & ~255
             rc = L.nr_rasterize_forward(
                 ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
-                _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal),
+                _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
                 ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
                 ctypes.c_void_p(sc.stats.data_ptr()), sc.event, ctypes.c_void_p(stream))
             _lib.check(rc, "nr_rasterize_forward")
@@ -122,7 +124,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
             if bad:
                 raise IndexError("faces reference a vertex index outside [0, %d)" % cfg.num_vertices)
             if not overflow:
-                return images, internal, fim, wmap, dmap
+                return images, internal, fim, wmap, dmap, tile_list
             capacity = int(total * 1.25) + 4096
         raise RuntimeError("tile pair list kept overflowing")
 
@@ -136,10 +138,10 @@ class _Rasterize(torch.autograd.Function):
         v = _f32c(vertices)
         vt = _f32c(vertices_textures) if vertices_textures is not None else None
         tex = _f32c(textures) if textures is not None else None
-        images, internal, fim, _, _ = _forward_call(cfg, v, faces, vt, faces_textures, tex, False)
+        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False)
         ctx.cfg = cfg
         ctx.has_tex = tex is not None
-        saved = [v, faces, fim, internal if internal is not None else images]
+        saved = [v, faces, fim, internal if internal is not None else images, tile_list]
         if ctx.has_tex:
             saved += [vt, faces_textures, tex]
         ctx.save_for_backward(*saved)
@@ -150,9 +152,9 @@ class _Rasterize(torch.autograd.Function):
         cfg = ctx.cfg
         L = _lib.lib()
         if ctx.has_tex:
-            v, faces, fim, internal, vt, ft, tex = ctx.saved_tensors
+            v, faces, fim, internal, tile_list, vt, ft, tex = ctx.saved_tensors
         else:
-            v, faces, fim, internal = ctx.saved_tensors
+            v, faces, fim, internal, tile_list = ctx.saved_tensors
             vt = ft = tex = None
         g = _f32c(grad_images)
         need_v, need_vt, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -163,7 +165,7 @@ class _Rasterize(torch.autograd.Function):
             gvt = torch.zeros_like(vt) if (need_vt and vt is not None) else None
             gtex = torch.zeros_like(tex) if (need_tex and tex is not None) else None
             rc = L.nr_rasterize_backward(ctypes.byref(cfg), _ptr(v), _ptr(faces), _ptr(vt), _ptr(ft),
-                                         _ptr(tex), _ptr(fim), _ptr(internal), _ptr(g), _ptr(gv),
+                                         _ptr(tex), _ptr(fim), _ptr(internal), _ptr(tile_list), _ptr(g), _ptr(gv),
                                          _ptr(gtex), _ptr(gvt), ctypes.c_void_p(stream))
             _lib.check(rc, "nr_rasterize_backward")
         return (gv if need_v else None), gvt, gtex, None, None, None
@@ -217,7 +219,7 @@ def rasterize_maps(vertices, faces, params: RasterizeParam, hyperparams: Rasteri
     (``face_index_map`` :235, ``weight_map`` :236, depth :292) plus the images.  Test / debug aid."""
     cfg, faces_d, vt, ft, tex = _prepare(vertices, faces, params, hyperparams)
     with torch.no_grad():
-        images, internal, fim, wmap, dmap = _forward_call(
+        images, internal, fim, wmap, dmap, _ = _forward_call(
             cfg, _f32c(vertices), faces_d, _f32c(vt) if vt is not None else None, ft,
             _f32c(tex) if tex is not None else None, True)
     return dict(images=images, internal_images=internal if internal is not None else images,

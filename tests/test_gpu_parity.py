@@ -183,6 +183,24 @@ def test_non_finite_vertices(nr):
     _check_vs_oracle(nr, f, 96)
 
 
+def test_vertices_on_pixel_centres(nr):
+    """Edges through pixel centres make edge functions exactly zero; the reference then accepts
+    every pixel of the bounding box lying on the line through v1-v2 (c2 == 0 passes both product
+    tests, rasterize_cuda_kernel.cu:109,114).  The tile / block culling must keep those pixels."""
+    R = 64
+    rng = np.random.RandomState(12)
+    for size in (6, 20, 40):
+        centre = rng.randint(0, R, size=(2, 600, 1, 2))
+        px = np.clip(centre + rng.randint(-size, size + 1, size=(2, 600, 3, 2)), -8, R + 8)
+        xy = (2. * px + 1 - R) / R
+        z = rng.uniform(1., 3., size=(2, 600, 3, 1))
+        f = np.concatenate([xy, z], -1).astype(np.float32)
+        f[:, :50, 1, 0] = f[:, :50, 2, 0]          # vertical edge v1-v2 on a pixel column
+        f[:, 50:100, 1, 1] = f[:, 50:100, 2, 1]    # horizontal edge v1-v2 on a pixel row
+        _check_vs_oracle(nr, f, R)
+        _check_vs_oracle(nr, f, R, backside=False)
+
+
 def test_near_far_clipping(nr):
     f = random_triangles(2, 2000, 6, size=0.1, zlo=0.05, zhi=4.0)
     _check_vs_oracle(nr, f, 128, near=1.0, far=2.5)
