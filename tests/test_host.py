@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: API surface, parameter defaults, camera math, input checks."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import neural_renderer_v2_pytorch_b200 as nr
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_public_names_of_the_reference_path():
+    # neural_renderer_torch/__init__.py:1-12, the names on the rasterize path
+    for name in ("load_obj", "look", "look_at", "perspective", "rasterize_silhouettes", "rasterize_rgba",
+                 "rasterize_rgb", "rasterize_depth", "Renderer", "to_gpu", "create_textures",
+                 "get_points_from_angles", "differentiation", "RasterizeParam", "RasterizeHyperparam"):
+        assert hasattr(nr, name), name
+
+
+def test_defaults_match_the_reference():
+    hp = nr.RasterizeHyperparam()          # rasterize_param.py:13-33
+    assert (hp.image_size, hp.near, hp.far, hp.eps) == (256, 0.1, 100.0, 1e-5)
+    assert hp.anti_aliasing and hp.draw_backside and hp.draw_rgb and hp.draw_silhouettes and hp.draw_depth
+    p = nr.RasterizeParam()
+    assert all(getattr(p, k) is None for k in ("vertices_textures", "faces_textures", "textures",
+                                               "background_color", "backgrounds", "lights"))
+    r = nr.Renderer()                      # renderer.py:8-22
+    assert (r.image_size, r.anti_aliasing, r.draw_backside, r.perspective, r.viewing_angle) == (256, True, True, True, 30)
+    assert r.camera_mode == "look_at" and r.near == 0.1 and r.far == 100
+    assert r.viewpoints == [0, 0, -(1. / math.tan(math.radians(30)) + 1)]
+
+
+def test_perspective_known_answer():
+    # tests_torch/test_perspective.py style: x / z / tan(angle)
+    v = torch.tensor([[[1., 2., 4.], [-3., 0.5, 2.]]])
+    out = nr.perspective(v, angle=30.)
+    w = math.tan(30 / 180. * 3.1416)
+    want = torch.tensor([[[1 / 4. / w, 2 / 4. / w, 4.], [-3 / 2. / w, 0.5 / 2. / w, 2.]]])
+    assert torch.allclose(out, want, rtol=1e-6)
+    assert nr.perspective(v, angle=torch.tensor(30.)).shape == v.shape
+
+
+def test_look_at_known_answers():
+    # tests_torch/test_look_at.py: eye on -z looking at the origin leaves x, y and shifts z
+    v = torch.tensor([[[1., 0., 0.], [0., 1., 0.], [0., 0., 1.]]])
+    out = nr.look_at(v, [0, 0, -2.])
+    assert torch.allclose(out, torch.tensor([[[1., 0., 2.], [0., 1., 2.], [0., 0., 3.]]]), atol=1e-6)
+    out = nr.look_at(v, [2., 0, 0])       # eye on +x: world -x becomes +z
+    assert torch.allclose(out[0, 0], torch.tensor([0., 0., 1.]), atol=1e-6)
+    eyes = torch.tensor([[0., 0., -2.], [2., 0., 0.]])
+    out = nr.look_at(v.repeat(2, 1, 1), eyes)
+    assert out.shape == (2, 3, 3)
+
+
+def test_get_points_from_angles():
+    x, y, z = nr.get_points_from_angles(2.0, 0., 0.)
+    assert abs(x) < 1e-12 and abs(y) < 1e-12 and abs(z + 2.0) < 1e-12
+    t = nr.get_points_from_angles(torch.tensor([2.0, 1.0]), torch.tensor([0., 90.]), torch.tensor([90., 0.]))
+    assert t.shape == (2, 3)
+    assert torch.allclose(t, torch.tensor([[2., 0., 0.], [0., 1., 0.]]), atol=1e-6)
+
+
+def test_create_textures_layout():
+    vt, ft, tex = nr.create_textures(2464, 4)
+    assert vt.shape == (7392, 2) and ft.shape == (2464, 3) and tex.shape == (3, 200, 200)
+    assert vt.dtype == np.float32 and ft.dtype == np.int32
+    assert vt.max() <= 199 and (ft == np.arange(7392).reshape(-1, 3)).all()
+    # face 51 -> tile (row 1, col 1) with tile_width 50
+    assert (vt[51 * 3] == [4, 4]).all() and (vt[51 * 3 + 1] == [4, 7]).all() and (vt[51 * 3 + 2] == [7, 7]).all()
+    vt, ft, tex = nr.create_textures(5, 2, flatten=True)
+    assert tex.shape == (3, 10, 2)
+
+
+def test_load_obj_matches_reference_loader(tmp_path):
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    p = tmp_path / "m.obj"
+    with open(p, "w") as f:
+        f.write("# quad + triangle\nv 0 0 0\nv 2 0 0\nv 2 1 0\nv 0 1 0\nv 1 3 1\n\nf 1 2 3 4\nf 4/1 3/2 5/3\n")
+    v, faces = nr.load_obj(str(p), normalization=False)
+    assert v.shape == (5, 3) and faces.tolist() == [[0, 1, 2], [0, 2, 3], [3, 2, 4]]
+    vn, _ = nr.load_obj(str(p))
+    assert np.abs(vn).max() <= 1.0 + 1e-6
+    assert d["vertices"].shape == (1292, 3) and d["faces"].shape == (2464, 3)
+
+
+def test_cpu_tensors_are_rejected_not_computed():
+    """No CPU fallback: a CPU tensor raises like CHECK_CUDA (rasterize_cuda.cpp:5)."""
+    hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False)
+    v = torch.zeros(1, 3, 3)
+    f = torch.tensor([[0, 1, 2]], dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        nr.rasterize_silhouettes(v, f, nr.RasterizeParam(), hp)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        nr.face_index_map_forward_safe(torch.zeros(1, 1, 3, 3), torch.zeros(256, dtype=torch.int32), 1, 16, 0.1, 100.,
+                                       1, 1e-8, 1e-4)
+    with pytest.raises(AssertionError):
+        nr.rasterize_silhouettes(torch.zeros(3, 3), f, nr.RasterizeParam(), hp)
+    with pytest.raises(AssertionError):
+        nr.rasterize_silhouettes(v, torch.zeros(1, 4, dtype=torch.int32), nr.RasterizeParam(), hp)
+
+
+def test_draw_flags_are_set_like_the_reference():
+    hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False)
+    with pytest.raises(RuntimeError):
+        nr.rasterize_depth(torch.zeros(1, 3, 3), torch.tensor([[0, 1, 2]]), nr.RasterizeParam(), hp)
+    assert (hp.draw_rgb, hp.draw_silhouettes, hp.draw_depth) == (False, False, True)   # rasterize.py:360-362
+    assert hp.image_size == 16
+
+
+def test_out_of_scope_features_say_so():
+    from neural_renderer_v2_pytorch_b200.rasterize import _prepare
+    hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False, draw_rgb=False, draw_depth=False)
+    v = torch.zeros(1, 3, 3)
+    f = torch.tensor([[0, 1, 2]])
+    for p in (nr.RasterizeParam(lights=[object()]), nr.RasterizeParam(background_color=[0, 0, 0]),
+              nr.RasterizeParam(backgrounds=torch.zeros(1, 3, 16, 16))):
+        with pytest.raises((NotImplementedError, RuntimeError)):
+            _prepare(v, f, p, hp)
+
+
+def test_bench_bytes_formula():
+    import bench
+    fwd, bwd = bench.algorithmic_bytes(nv=1292, nf=2464, T=40000, P=512 * 512, C=4, S=512)
+    assert abs((fwd + bwd) / 1e6 - 18.28) < 0.01
+    fwd, bwd = bench.algorithmic_bytes(nv=1292, nf=2464, T=0, P=512 * 512, C=1, S=512)
+    assert abs((fwd + bwd) / 1e6 - 10.55) < 0.03
