@@ -81,6 +81,32 @@ int check_config(const nrRasterConfig *cfg) {
     return NR_OK;
 }
 
+// per-device side stream: the background fill of the outputs does not depend on the binning
+// kernels, so it runs next to them (fork / join with two events) instead of in front of the raster
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::mutex g_side_mu;
+SideStream g_side[64];
+
+SideStream *side_stream() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    SideStream &s = g_side[dev];
+    if (!s.stream) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            s.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &s;
+}
+
 // per-device scratch for the two reference-signature operators
 struct CompatScratch {
     void *ptr = nullptr;
@@ -170,16 +196,6 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.hdr = c.hdr;
     ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
-    cudaError_t e = nr::launch_binning(ba, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "binning");
-    if (stats_host) {
-        e = cudaMemcpyAsync(stats_host, c.hdr, sizeof(nrBinStats), cudaMemcpyDeviceToHost, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "stats copy");
-    }
-    if (stats_event) {
-        e = cudaEventRecord((cudaEvent_t)stats_event, stream);
-        if (e != cudaSuccess) return fail_cuda(e, "stats event");
-    }
 
     nr::RasterArgs ra;
     ra.rec = c.rec;
@@ -211,6 +227,30 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.dmap = depth_map;
     ra.images = images;
     ra.internal = images_internal;
+
+    // fork: background fill on the side stream, binning on the caller's stream
+    cudaError_t e;
+    SideStream *side = side_stream();
+    if (side) {
+        if ((e = cudaEventRecord(side->fork, stream)) != cudaSuccess) return fail_cuda(e, "fork");
+        if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return fail_cuda(e, "fork wait");
+        if ((e = nr::launch_background_fill(ra, side->stream)) != cudaSuccess) return fail_cuda(e, "background fill");
+        if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return fail_cuda(e, "join");
+    } else if ((e = nr::launch_background_fill(ra, stream)) != cudaSuccess) {
+        return fail_cuda(e, "background fill");
+    }
+
+    e = nr::launch_binning(ba, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "binning");
+    if (stats_host) {
+        e = cudaMemcpyAsync(stats_host, c.hdr, sizeof(nrBinStats), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "stats copy");
+    }
+    if (stats_event) {
+        e = cudaEventRecord((cudaEvent_t)stats_event, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "stats event");
+    }
+    if (side && (e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return fail_cuda(e, "join wait");
     e = nr::launch_raster(ra, stream);
     if (e != cudaSuccess) return fail_cuda(e, "raster");
     return NR_OK;

@@ -190,81 +190,89 @@ k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restri
         }
 }
 
-// Ascending in-place sort of every tile list of up to SMEM_SORT_CAP faces: one warp per tile,
-// grid-stride over the work list.  The scatter kernel mostly claims slots in face order already, so
-// most lists only pay the sortedness check.  Lists of <= 32 ids are rank-sorted in registers,
-// longer ones with a same-direction bitonic network in this warp's slice of shared memory.
+// Ascending in-place sort of every tile list of up to SMEM_SORT_CAP faces, grid-stride over the work
+// list.  Lists that the scatter kernel happened to fill in face order only pay the sortedness check.
+// Lists of <= 64 ids are rank-sorted in registers by one warp (two ids per lane); longer ones by
+// the whole CTA with a bitonic network in shared memory.
 constexpr int SORT_WARPS = 4;
+constexpr int SORT_WARP_MAX = 64;     // lists up to this length: one warp each
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
              const BinHeader *__restrict__ hdr) {
-    __shared__ int s_ids[SORT_WARPS][SMEM_SORT_CAP];
+    __shared__ int s_ids[SMEM_SORT_CAP];
     if (hdr->overflow) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int count = tile_list[0];
     const int4 *entries = reinterpret_cast<const int4 *>(tile_list + TILE_LIST_HDR);
+
+    // ---- pass A: short lists, one warp per list
     for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
         const int4 e = entries[w];
         const int n = e.w;
-        if (n < 2 || n > SMEM_SORT_CAP) continue;
+        if (n < 2 || n > SORT_WARP_MAX) continue;
         int32_t *a = pairs + e.z;
-        if (n <= 32) {
-            const int v = lane < n ? a[lane] : 0x7fffffff;
-            const int nxt = __shfl_down_sync(0xffffffffu, v, 1);
-            if (__ballot_sync(0xffffffffu, lane < 31 && v > nxt) == 0u) continue;
-            int rank = 0;
+        // two ids per lane: positions lane and lane + 32
+        const int v0 = lane < n ? a[lane] : 0x7fffffff;
+        const int v1 = lane + 32 < n ? a[lane + 32] : 0x7fffffff;
+        const int nx0 = __shfl_down_sync(0xffffffffu, v0, 1), nx1 = __shfl_down_sync(0xffffffffu, v1, 1);
+        const int first1 = __shfl_sync(0xffffffffu, v1, 0);
+        const bool bad = (lane < 31 ? v0 > nx0 : v0 > first1) || (lane < 31 && v1 > nx1);
+        if (__ballot_sync(0xffffffffu, bad) == 0u) continue;
+        int r0 = 0, r1 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rank += (__shfl_sync(0xffffffffu, v, j) < v);
-            if (lane < n) a[rank] = v;     // ids are unique inside one list
-            continue;
+        for (int j = 0; j < 32; ++j) {
+            const int x = __shfl_sync(0xffffffffu, v0, j), y = __shfl_sync(0xffffffffu, v1, j);
+            r0 += (x < v0) + (y < v0);
+            r1 += (x < v1) + (y < v1);
         }
-        int *sm = s_ids[wid];
-        int unsorted = 0;
-        for (int i = lane; i < n; i += 32) sm[i] = a[i];
         __syncwarp();
-        for (int i = lane; i + 1 < n; i += 32) unsorted |= (sm[i] > sm[i + 1]);
-        if (__ballot_sync(0xffffffffu, unsorted) == 0u) continue;
-        if (n <= 64) {
-            // rank sort straight from the shared copy into global memory
-            for (int i = lane; i < n; i += 32) {
-                const int v = sm[i];
-                int rank = 0;
-                for (int j = 0; j < n; ++j) rank += (sm[j] < v);
-                a[rank] = v;
-            }
-            __syncwarp();
-            continue;
-        }
-        int lg = 6;
-        while ((1 << lg) < n) ++lg;
-        const int half = 1 << (lg - 1);
-        for (int kk = 1; kk <= lg; ++kk) {
-            const int k = 1 << kk;
-            for (int i = lane; i < half; i += 32) {
-                const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
-                const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
-                if (hi < n && sm[lo] > sm[hi]) {
-                    const int t = sm[lo];
-                    sm[lo] = sm[hi];
-                    sm[hi] = t;
-                }
-            }
-            __syncwarp();
-            for (int jj = kk - 2; jj >= 0; --jj) {
-                const int j = 1 << jj;
-                for (int i = lane; i < half; i += 32) {
-                    const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
-                    if (hi < n && sm[lo] > sm[hi]) {
-                        const int t = sm[lo];
-                        sm[lo] = sm[hi];
-                        sm[hi] = t;
+        if (lane < n) a[r0] = v0;          // ids are unique inside one list
+        if (lane + 32 < n) a[r1] = v1;
+    }
+
+    // ---- pass B: longer lists, the whole CTA per list (same-direction bitonic network over a
+    // virtual power-of-two length: indices >= n behave as +inf and never move)
+    for (int w = blockIdx.x; w < count; w += gridDim.x) {
+        const int4 e = entries[w];
+        const int n = e.w;
+        if (n <= SORT_WARP_MAX || n > SMEM_SORT_CAP) continue;      // CTA-uniform
+        int32_t *a = pairs + e.z;
+        int unsorted = 0;
+        for (int i = tid; i < n; i += blockDim.x) s_ids[i] = a[i];
+        __syncthreads();
+        for (int i = tid; i + 1 < n; i += blockDim.x) unsorted |= (s_ids[i] > s_ids[i + 1]);
+        if (__syncthreads_or(unsorted)) {
+            int lg = 7;
+            while ((1 << lg) < n) ++lg;
+            const int half = 1 << (lg - 1);
+            for (int kk = 1; kk <= lg; ++kk) {
+                const int k = 1 << kk;
+                for (int i = tid; i < half; i += blockDim.x) {
+                    const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
+                    const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
+                    if (hi < n && s_ids[lo] > s_ids[hi]) {
+                        const int t = s_ids[lo];
+                        s_ids[lo] = s_ids[hi];
+                        s_ids[hi] = t;
                     }
                 }
-                __syncwarp();
+                __syncthreads();
+                for (int jj = kk - 2; jj >= 0; --jj) {
+                    const int j = 1 << jj;
+                    for (int i = tid; i < half; i += blockDim.x) {
+                        const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
+                        if (hi < n && s_ids[lo] > s_ids[hi]) {
+                            const int t = s_ids[lo];
+                            s_ids[lo] = s_ids[hi];
+                            s_ids[hi] = t;
+                        }
+                    }
+                    __syncthreads();
+                }
             }
+            for (int i = tid; i < n; i += blockDim.x) a[i] = s_ids[i];
         }
-        for (int i = lane; i < n; i += 32) a[i] = sm[i];
-        __syncwarp();
+        __syncthreads();
     }
 }
 

@@ -54,6 +54,7 @@ struct RasterArgs {
     float *images;          // [B, C, S, S] or null (compat call renders no image)
     float *internal;        // [B, C, R, R] (AA) or null
 };
+cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream);
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);
 
 struct BackwardArgs {

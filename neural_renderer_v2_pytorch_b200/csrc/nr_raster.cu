@@ -170,6 +170,8 @@ k_raster(const RasterArgs a) {
             }
             __syncwarp();
             const int nh = __popc(m);
+            // ---- phase 1: coverage of every surviving face, one bit per face (cheap, all lanes)
+            unsigned inside = 0u;
             for (int j = 0; j < nh; ++j) {
                 const uint2 bb = my_bb[j];
                 // :94-97, exact by construction of the pixel box
@@ -183,9 +185,18 @@ k_raster(const RasterArgs a) {
                 if (__fmul_rn(c1, c2) < 0.f) continue;
                 const float c3 = __fmaf_rn(__fsub_rn(yp, Bq.y), Cq.z, -__fmul_rn(Cq.w, __fsub_rn(xp, Bq.x)));
                 if (__fmul_rn(c2, c3) < 0.f) continue;
+                inside |= 1u << j;
+            }
+            // ---- phase 2: every lane walks ITS OWN covering faces in list order (the z-test is
+            // sequential per pixel only), so lanes evaluate different faces at the same time and the
+            // loop runs max-depth-complexity times instead of once per surviving face
+            while (inside) {
+                const int j = __ffs(inside) - 1;
+                inside &= inside - 1;
                 const float4 D = my_rec[j][3];
                 // :124-126
                 if (depth_min < D.x && depth_min < D.y && depth_min < D.z) continue;
+                const float4 A = my_rec[j][0], Bq = my_rec[j][1];
                 // :129-136
                 float w0, w1, w2;
                 raw_weights(xp, yp, A.x, A.y, A.z, A.w, Bq.x, Bq.y, w0, w1, w2);
@@ -302,20 +313,23 @@ k_weight_map_compat(const float *__restrict__ faces, const int32_t *__restrict__
     wmap[i * 3 + 2] = w2;
 }
 
+// Background everywhere (face index -1, zeros elsewhere); the raster kernel then writes foreground
+// pixels only.  Independent of the binning kernels, so the caller runs it on a side stream.
+cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream) {
+    if (a.B <= 0 || a.R <= 0) return cudaSuccess;
+    ProfScope p(PROF_MEMSET, stream);
+    const size_t P = (size_t)a.B * a.R * a.R;
+    cudaError_t e = cudaMemsetAsync(a.fim, 0xff, P * sizeof(int32_t), stream);   // -1
+    if (e == cudaSuccess && a.wmap) e = cudaMemsetAsync(a.wmap, 0, P * 3 * sizeof(float), stream);
+    if (e == cudaSuccess && a.dmap) e = cudaMemsetAsync(a.dmap, 0, P * sizeof(float), stream);
+    if (e == cudaSuccess && a.images)
+        e = cudaMemsetAsync(a.images, 0, (size_t)a.B * a.C * a.S * a.S * sizeof(float), stream);
+    if (e == cudaSuccess && a.images && a.internal) e = cudaMemsetAsync(a.internal, 0, P * a.C * sizeof(float), stream);
+    return e;
+}
+
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
-    // background everywhere first; the kernel then writes foreground pixels only
-    {
-        ProfScope p(PROF_MEMSET, stream);
-        const size_t P = (size_t)a.B * a.R * a.R;
-        cudaError_t e = cudaMemsetAsync(a.fim, 0xff, P * sizeof(int32_t), stream);   // -1
-        if (e == cudaSuccess && a.wmap) e = cudaMemsetAsync(a.wmap, 0, P * 3 * sizeof(float), stream);
-        if (e == cudaSuccess && a.dmap) e = cudaMemsetAsync(a.dmap, 0, P * sizeof(float), stream);
-        if (e == cudaSuccess && a.images)
-            e = cudaMemsetAsync(a.images, 0, (size_t)a.B * a.C * a.S * a.S * sizeof(float), stream);
-        if (e == cudaSuccess && a.images && a.internal) e = cudaMemsetAsync(a.internal, 0, P * a.C * sizeof(float), stream);
-        if (e != cudaSuccess) return e;
-    }
     const long long tiles = (long long)a.ntx * a.ntx * a.B;
     const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
     ProfScope p(PROF_RASTER, stream);
