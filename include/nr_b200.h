@@ -75,10 +75,11 @@ typedef struct nrRasterConfig {
 
 /*
  * Written by the forward into the workspace header and, when `stats_host` is given,
- * copied asynchronously to that (pinned) host struct so the caller can check it after
- * synchronising on its own event.  overflow != 0 means the (tile, face) pair list did
- * not fit `pair_capacity`: the outputs of that call are undefined; call again with a
- * workspace sized for at least `total_pairs`.
+ * copied asynchronously to that (pinned) host struct so the caller can look at it once
+ * `stats_event` has completed.  overflow != 0 means the (tile, face) pair list did not fit
+ * `pair_capacity`: the results of that call are STILL CORRECT (the raster kernel then scans
+ * every face of the view per pixel block, like the reference does) but slow; size the next
+ * call's workspace for at least `total_pairs`.  No host synchronisation is ever required.
  */
 typedef struct nrBinStats {
     int32_t total_pairs;      /* sum over tiles of faces whose pixel bbox touches the tile */
@@ -97,6 +98,7 @@ NR_API int nr_num_channels(int32_t flags);
 NR_API int nr_event_create(void **event);
 NR_API int nr_event_destroy(void *event);
 NR_API int nr_event_synchronize(void *event);
+NR_API int nr_event_query(void *event); /* 1 complete, 0 not yet, -1 error */
 
 /*
  * Per-kernel timing hook for bench.py: while enabled, every kernel this library launches is

@@ -26,7 +26,7 @@ NR_DETERMINISTIC = 32
 # every symbol include/nr_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (
     "nr_abi_version", "nr_last_error", "nr_num_channels", "nr_event_create", "nr_event_destroy",
-    "nr_event_synchronize", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
+    "nr_event_synchronize", "nr_event_query", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
     "nr_differentiation_backward", "nr_face_index_map_forward_safe", "nr_compute_weight_map",
     "nr_profile_enable", "nr_profile_collect",
 )
@@ -95,6 +95,8 @@ def lib():
     L.nr_event_destroy.argtypes = [vp]
     L.nr_event_synchronize.restype = ctypes.c_int
     L.nr_event_synchronize.argtypes = [vp]
+    L.nr_event_query.restype = ctypes.c_int
+    L.nr_event_query.argtypes = [vp]
     L.nr_workspace_bytes.restype = ctypes.c_size_t
     L.nr_workspace_bytes.argtypes = [ctypes.POINTER(RasterConfig), i64]
     L.nr_rasterize_forward.restype = ctypes.c_int

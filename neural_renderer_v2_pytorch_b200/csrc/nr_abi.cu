@@ -142,6 +142,14 @@ int nr_event_destroy(void *event) {
     cudaError_t e = cudaEventDestroy((cudaEvent_t)event);
     return e == cudaSuccess ? NR_OK : fail_cuda(e, "cudaEventDestroy");
 }
+int nr_event_query(void *event) {
+    if (!event) return -1;
+    cudaError_t e = cudaEventQuery((cudaEvent_t)event);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    fail_cuda(e, "cudaEventQuery");
+    return -1;
+}
 int nr_event_synchronize(void *event) {
     if (!event) return fail(NR_ERR_INVALID_ARGUMENT, "event is NULL");
     cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);

@@ -85,6 +85,7 @@ __device__ __forceinline__ void clamp_shares(float x0, float lo, float hi, float
 
 // Backward of sample_texture(): returns the four tap indices (-1 when the tap reads as zero),
 // the tap weights, and the gradients w.r.t. face depths and corner uv's.
+template <bool NEED_UV>
 __device__ __forceinline__ void sample_texture_backward(const float *__restrict__ tex_b, int H, int W,
                                                         float eps, const float q[3], const float z[3],
                                                         const float u[3], const float v[3],
@@ -114,7 +115,7 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
     }
     const float gxf = ay * (d[1] - d[0]) + by * (d[3] - d[2]);
     const float gyf = ax * (d[2] - d[0]) + bx * (d[3] - d[1]);
-    float sx, sxlo, sxhi, sy, sylo, syhi;
+    float sx, sxlo = 0.f, sxhi = 0.f, sy, sylo = 0.f, syhi = 0.f;
     clamp_shares(x0, ulo, uhi, sx, sxlo, sxhi);
     clamp_shares(y0, vlo, vhi, sy, sylo, syhi);
     const float gx0 = gxf * sx, gy0 = gyf * sy;
@@ -124,15 +125,19 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float iz = 1.f / zz[k];
-        gu[k] = gnx * q[k] * iz;
-        gv[k] = gny * q[k] * iz;
+        if (NEED_UV) {
+            gu[k] = gnx * q[k] * iz;
+            gv[k] = gny * q[k] * iz;
+        }
         gz[k] = -(gnx * q[k] * u[k] + gny * q[k] * v[k] + gD * q[k]) * iz * iz;
     }
-    // clamp bounds depend on the corner uv's themselves (min / max over the corners)
-    gu[first_argmin3(u)] += gxf * sxlo;
-    gu[first_argmax3(u)] += gxf * sxhi;
-    gv[first_argmin3(v)] += gyf * sylo;
-    gv[first_argmax3(v)] += gyf * syhi;
+    if (NEED_UV) {
+        // clamp bounds depend on the corner uv's themselves (min / max over the corners)
+        gu[first_argmin3(u)] += gxf * sxlo;
+        gu[first_argmax3(u)] += gxf * sxhi;
+        gv[first_argmin3(v)] += gyf * sylo;
+        gv[first_argmax3(v)] += gyf * syhi;
+    }
 }
 
 // Warp-level segmented sum over runs of equal `key` in lane order (a warp is one image row
@@ -144,12 +149,13 @@ __device__ __forceinline__ bool run_reduce(int key, bool valid, float (&v)[N], i
     const int prev = __shfl_up_sync(0xffffffffu, key, 1);
     const bool prev_valid = __shfl_up_sync(0xffffffffu, (int)valid, 1) != 0;
     // an invalid lane is a run of its own and separates the runs around it
-    const bool head = (lane == 0) || !valid || !prev_valid || (key != prev);
+    // runs never cross lane 16 (a warp holds two 16-pixel rows), so four doubling steps suffice
+    const bool head = ((lane & 15) == 0) || !valid || !prev_valid || (key != prev);
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     if (heads != 0xffffffffu) {
         const int seg_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int d = 1; d < 16; d <<= 1) {
             const bool take = (lane - d >= seg_start);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -164,7 +170,7 @@ __device__ __forceinline__ bool run_reduce(int key, bool valid, float (&v)[N], i
 // C = channel count at compile time (0: read it from the arguments).
 // Persistent over the forward's list of non-empty 16x16 tiles (grid-stride); a warp owns two
 // 16-pixel row segments of the tile, so the pixels of one face form runs in lane order.
-template <int CT>
+template <int CT, bool NEED_UV>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_backward(const BackwardArgs a) {
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
@@ -284,15 +290,15 @@ k_backward(const BackwardArgs a) {
                     u[k] = uv.x;
                     v[k] = uv.y;
                 }
-                float gu[3], gv[3], tw[4];
-                sample_texture_backward(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g,
+                float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f}, tw[4];
+                sample_texture_backward<NEED_UV>(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g,
                                         tap, tw, cell, gz, gu, gv);
                 has_tex = true;
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) tg[t * 3 + c] = tw[t] * g[c];
-                if (a.grad_vt) {
+                if (NEED_UV) {
                     float *gvt = a.grad_vt + (size_t)b * a.nvt * 2;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -387,11 +393,15 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
     dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
-    switch (a.C) {
-        case 1: k_backward<1><<<grid, block, 0, stream>>>(a); break;
-        case 3: k_backward<3><<<grid, block, 0, stream>>>(a); break;
-        case 4: k_backward<4><<<grid, block, 0, stream>>>(a); break;
-        default: k_backward<0><<<grid, block, 0, stream>>>(a); break;
+    if (a.grad_vt) {
+        k_backward<0, true><<<grid, block, 0, stream>>>(a);
+    } else {
+        switch (a.C) {
+            case 1: k_backward<1, false><<<grid, block, 0, stream>>>(a); break;
+            case 3: k_backward<3, false><<<grid, block, 0, stream>>>(a); break;
+            case 4: k_backward<4, false><<<grid, block, 0, stream>>>(a); break;
+            default: k_backward<0, false><<<grid, block, 0, stream>>>(a); break;
+        }
     }
     return cudaGetLastError();
 }

@@ -96,7 +96,10 @@ k_raster(const RasterArgs a) {
     __shared__ float4 s_rec[RASTER_WARPS][32][4];
     __shared__ uint2 s_bb[RASTER_WARPS][32];
 
-    if (a.hdr->overflow) return;
+    // If the pair list did not fit the workspace, the lists are unusable: every block then scans ALL
+    // faces of its view (the records are complete regardless), which is the reference's own loop with
+    // the block cull in front.  Slow but correct, and the host grows the workspace for the next call.
+    const bool overflow = a.hdr->overflow != 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int R = a.R;
     const int count = a.tile_list[0];
@@ -121,7 +124,7 @@ k_raster(const RasterArgs a) {
     for (int item = first; item < min(first + GRAB, items); ++item) {
         const int4 e0 = __ldg(entries + (item >> 3));
         const int sub = item & 7;
-        const int b = e0.x, n = e0.w;
+        const int b = e0.x, n = overflow ? a.nf : e0.w;
         const int32_t *list = a.pairs + e0.z;
         const int wx0 = (e0.y & 0xffff) * TILE + (sub & 1) * WARP_BW, wx1 = wx0 + WARP_BW - 1;
         const int wy0 = (e0.y >> 16) * TILE + (sub >> 1) * WARP_BH, wy1 = wy0 + WARP_BH - 1;
@@ -146,7 +149,7 @@ k_raster(const RasterArgs a) {
             int fid = -1;
             float4 q0, q1, q2;
             if (g + lane < n) {
-                fid = __ldg(list + g + lane);
+                fid = overflow ? g + lane : __ldg(list + g + lane);
                 const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid);
                 q0 = __ldg(rp);
                 q1 = __ldg(rp + 1);

@@ -20,6 +20,9 @@ from .rasterize_param import RasterizeParam, RasterizeHyperparam
 
 DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
 
+# test hook: force the (tile, face) pair capacity (e.g. 0) to exercise the device-side overflow path
+FORCE_PAIR_CAPACITY = None
+
 
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor):
@@ -43,7 +46,10 @@ def _ptr(t):
 
 class _Scratch:
     """Per (device, stream) scratch: workspace bytes, pinned bin statistics, a CUDA event.
-    The (tile, face) pair capacity grows on demand and is remembered."""
+
+    The forward never waits for the GPU.  The bin statistics of call k are read when call k+1
+    (or later) finds their event complete; if the (tile, face) pair list overflowed, call k was
+    still correct (device-side fallback, see nr_b200.h) and the capacity grows for the next call."""
 
     _cache = {}
 
@@ -52,6 +58,8 @@ class _Scratch:
         self.workspace = None
         self.pair_capacity = 0
         self.stats = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.pending = False
+        self.overflows = 0
         ev = ctypes.c_void_p()
         _lib.check(_lib.lib().nr_event_create(ctypes.byref(ev)), "nr_event_create")
         self.event = ev
@@ -63,6 +71,21 @@ class _Scratch:
         if s is None:
             s = cls._cache[key] = cls(device)
         return s
+
+    def poll(self, block=False):
+        """Fold the statistics of the last launched forward into the capacity, if they have arrived."""
+        if not self.pending:
+            return
+        L = _lib.lib()
+        if block:
+            _lib.check(L.nr_event_synchronize(self.event), "nr_event_synchronize")
+        elif L.nr_event_query(self.event) != 1:
+            return
+        self.pending = False
+        total, _max_tile, overflow, _bad = self.stats.tolist()
+        if overflow:
+            self.overflows += 1
+            self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
 
     def ensure(self, cfg, capacity):
         need = _lib.lib().nr_workspace_bytes(ctypes.byref(cfg), capacity)
@@ -88,7 +111,7 @@ def _flags_of(hp):
 
 
 def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
-    """Runs nr_rasterize_forward, regrowing the pair list if it overflowed.
+    """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
     Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
     dev = vertices.device
@@ -99,6 +122,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         sc = _Scratch.get(dev, stream)
+        sc.poll()
         fim = torch.empty((B, R, R), dtype=torch.int32, device=dev)
         images = torch.empty((B, C, S, S), dtype=torch.float32, device=dev)
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
@@ -107,26 +131,43 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
         ntx = (R + 15) // 16
         tile_list = torch.empty(4 + 4 * B * ntx * ntx, dtype=torch.int32, device=dev)
         capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
-        for _ in range(4):
-            sc.ensure(cfg, capacity)
-            ws = sc.workspace
-            base = ws.data_ptr()
-            aligned = (base + 255) & ~255
-            rc = L.nr_rasterize_forward(
-                ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
-                _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
-                ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
-                ctypes.c_void_p(sc.stats.data_ptr()), sc.event, ctypes.c_void_p(stream))
-            _lib.check(rc, "nr_rasterize_forward")
-            # waits for the binning kernels only; the raster kernel is already queued behind them
-            _lib.check(L.nr_event_synchronize(sc.event), "nr_event_synchronize")
-            total, _max_tile, overflow, bad = sc.stats.tolist()
-            if bad:
-                raise IndexError("faces reference a vertex index outside [0, %d)" % cfg.num_vertices)
-            if not overflow:
-                return images, internal, fim, wmap, dmap, tile_list
-            capacity = int(total * 1.25) + 4096
-        raise RuntimeError("tile pair list kept overflowing")
+        if FORCE_PAIR_CAPACITY is not None:
+            capacity = int(FORCE_PAIR_CAPACITY)
+        if sc.pending:
+            # the pinned statistics are still owned by an earlier call in flight
+            sc.poll(block=sc.workspace is None or
+                    sc.workspace.numel() < L.nr_workspace_bytes(ctypes.byref(cfg), capacity))
+        sc.ensure(cfg, capacity)
+        ws = sc.workspace
+        base = ws.data_ptr()
+        aligned = (base + 255) & ~255
+        track = not sc.pending
+        rc = L.nr_rasterize_forward(
+            ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
+            _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
+            ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
+            ctypes.c_void_p(sc.stats.data_ptr()) if track else None, sc.event if track else None,
+            ctypes.c_void_p(stream))
+        _lib.check(rc, "nr_rasterize_forward")
+        if track:
+            sc.pending = True
+        return images, internal, fim, wmap, dmap, tile_list
+
+
+_validated_faces = {}
+
+
+def _validate_indices(idx, limit, what):
+    """Index range check with the reference's error type (IndexError from tensor indexing,
+    rasterize.py:232,246).  Costs one device->host read per distinct index tensor, then cached."""
+    key = (idx.data_ptr(), idx._version, tuple(idx.shape), limit)
+    if _validated_faces.get(what) == key:
+        return
+    if idx.numel():
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= limit:
+            raise IndexError("%s reference index %d outside [0, %d)" % (what, hi if hi >= limit else lo, limit))
+    _validated_faces[what] = key
 
 
 class _Rasterize(torch.autograd.Function):
@@ -184,9 +225,11 @@ def _prepare(vertices, faces, params, hyperparams):
         raise NotImplementedError("backgrounds are outside the accelerated path (and broken in the "
                                   "reference, rasterize.py:156-159)")
     dev = vertices.device
-    faces_d = _i32c(torch.as_tensor(faces)).to(dev)
+    faces = torch.as_tensor(faces)
+    faces_d = _i32c(faces).to(dev)
     B, nv = vertices.shape[:2]
     nf = faces_d.shape[0]
+    _validate_indices(faces, nv, "faces")
     vt = ft = tex = None
     nvt = H = W = 0
     if hyperparams.draw_rgb:
@@ -203,6 +246,7 @@ def _prepare(vertices, faces, params, hyperparams):
         assert params.faces_textures.shape[0] == nf
         ft = _i32c(torch.as_tensor(params.faces_textures)).to(dev)
         nvt, H, W = vt.shape[1], tex.shape[2], tex.shape[3]
+        _validate_indices(torch.as_tensor(params.faces_textures), nvt, "faces_textures")
     cfg = _make_config(B, nv, nf, int(hyperparams.image_size), _flags_of(hyperparams), hyperparams,
                        nvt, H, W)
     return cfg, faces_d, vt, ft, tex

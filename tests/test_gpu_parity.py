@@ -214,6 +214,27 @@ def test_long_tile_lists(nr):
     _check_vs_oracle(nr, f, 64)
 
 
+def test_pair_list_overflow_falls_back_on_device(nr):
+    """With no room for the (tile, face) pairs the forward must still be exact (every block scans all
+    faces of its view) and the host must grow the capacity from the lazily read statistics."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    d = np.load(os.path.join(GOLDEN, "case_rgba_64.npz"))
+    rz.FORCE_PAIR_CAPACITY = 0
+    try:
+        images, v, tex, vt, maps = run_cuda(nr, d)
+    finally:
+        rz.FORCE_PAIR_CAPACITY = None
+    assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
+    np.testing.assert_allclose(images.detach().cpu().numpy(), d["images"], rtol=1e-5, atol=1e-6)
+    grad_close(v.grad.cpu().numpy(), d["grad_vertices"], "grad_vertices")
+    torch.cuda.synchronize()
+    sc = rz._Scratch.get(torch.device("cuda", 0), torch.cuda.current_stream().cuda_stream)
+    sc.poll(block=True)
+    assert sc.overflows >= 1 and sc.pair_capacity > 0
+    images, v, tex, vt, maps = run_cuda(nr, d)      # regular path again
+    assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
+
+
 def test_teapot_views(nr):
     d = np.load(os.path.join(GOLDEN, "teapot.npz"))
     B = 4
