@@ -190,19 +190,31 @@ def run_ours(args):
             tex_dev.grad = None
         step(v_dev, tex_dev)
     barrier()
+    # the whole step (forward + backward, ~12 short launches) is captured once in a CUDA graph and
+    # replayed: every replay does the full work on the device; --eager launches from Python instead
+    if args.eager:
+        def run_step():
+            v_dev.grad = None
+            if rgb:
+                tex_dev.grad = None
+            return step(v_dev, tex_dev)
+    else:
+        run_step = nr.capture_step(lambda: step(v_dev, tex_dev), params=[v_dev] + ([tex_dev] if rgb else []), warmup=2)
+    for _ in range(3):
+        run_step()
+    barrier()
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        v_dev.grad = None
-        if rgb:
-            tex_dev.grad = None
-        step(v_dev, tex_dev)
+        run_step()
         if sampler and i == args.steps // 2:
             sampler.sample()
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -237,10 +249,12 @@ def run_ours(args):
     chk_host = torch.empty(1).pin_memory()
 
     def e2e_step():
-        v = v_host.to(dev, non_blocking=True).requires_grad_(True)
-        tex = tex_host.to(dev, non_blocking=True).requires_grad_(True) if rgb else None
-        images = step(v, tex)
-        gv_host.copy_(v.grad, non_blocking=True)
+        # host (pinned) -> device copies of this step's inputs, the step, device -> host of its results
+        v_dev.data.copy_(v_host, non_blocking=True)
+        if rgb:
+            tex_dev.data.copy_(tex_host, non_blocking=True)
+        images = run_step()
+        gv_host.copy_(v_dev.grad, non_blocking=True)
         chk_host.copy_(images.sum().reshape(1), non_blocking=True)
 
     for _ in range(3):
@@ -302,6 +316,8 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(round(launches_per_step * args.steps)),
+        "launch_mode": "eager (python)" if args.eager else "cuda graph replay of the whole step",
+        "host_ms_per_step": round(host_ms, 4),
         "clocks": clocks,
         "roofline": roofline,
         "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
@@ -405,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,6 +17,7 @@ from .rasterize import (rasterize_silhouettes, rasterize_rgba, rasterize_rgb, ra
 from .renderer import Renderer
 from .utils import to_gpu, create_textures, get_points_from_angles
 from .differentiation import differentiation
+from .graph import capture_step
 from . import parallel
 
 __version__ = '2.0.2+b200.1'

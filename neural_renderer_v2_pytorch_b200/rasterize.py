@@ -122,7 +122,11 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         sc = _Scratch.get(dev, stream)
-        sc.poll()
+        # inside a CUDA-graph capture nothing may query or synchronise: the statistics of the
+        # eager warm-up calls have already sized the workspace
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            sc.poll()
         fim = torch.empty((B, R, R), dtype=torch.int32, device=dev)
         images = torch.empty((B, C, S, S), dtype=torch.float32, device=dev)
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
@@ -133,15 +137,18 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
         capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
         if FORCE_PAIR_CAPACITY is not None:
             capacity = int(FORCE_PAIR_CAPACITY)
-        if sc.pending:
+        need_grow = sc.workspace is None or sc.workspace.numel() < L.nr_workspace_bytes(ctypes.byref(cfg), capacity)
+        if capturing and need_grow:
+            raise RuntimeError("run the step eagerly a few times before capturing it in a CUDA graph "
+                               "(the rasterizer sizes its workspace from those warm-up calls)")
+        if sc.pending and not capturing:
             # the pinned statistics are still owned by an earlier call in flight
-            sc.poll(block=sc.workspace is None or
-                    sc.workspace.numel() < L.nr_workspace_bytes(ctypes.byref(cfg), capacity))
+            sc.poll(block=need_grow)
         sc.ensure(cfg, capacity)
         ws = sc.workspace
         base = ws.data_ptr()
         aligned = (base + 255) & ~255
-        track = not sc.pending
+        track = not sc.pending and not capturing
         rc = L.nr_rasterize_forward(
             ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
@@ -163,6 +170,8 @@ def _validate_indices(idx, limit, what):
     key = (idx.data_ptr(), idx._version, tuple(idx.shape), limit)
     if _validated_faces.get(what) == key:
         return
+    if idx.is_cuda and torch.cuda.is_current_stream_capturing():
+        return      # cannot read back during capture; the kernels drop out-of-range faces anyway
     if idx.numel():
         lo, hi = int(idx.min()), int(idx.max())
         if lo < 0 or hi >= limit:
