@@ -33,6 +33,10 @@ WORKLOADS = {
     "cfg2s": dict(views=64, S=512, aa=False, mode="silhouettes", ts=0, mesh="teapot"),
     "cfg1": dict(views=1, S=256, aa=True, mode="rgba", ts=16, mesh="teapot"),
     "cfg5": dict(views=32, S=512, aa=True, mode="rgb", ts=4, mesh="teapot"),
+    # multi-view optimisation of ONE shared 100k-face mesh: gradient all-reduce across ranks
+    "cfg3": dict(views=8, S=512, aa=False, mode="silhouettes", ts=0, mesh="sphere", shared=True),
+    # 1M independent ~5 px triangles: stresses binning, list sorting and z-test contention
+    "cfg4": dict(views=16, S=1024, aa=False, mode="silhouettes", ts=0, mesh="random1m"),
 }
 METRIC = "megapixel-views/sec fwd+bwd"
 UNIT = "Mpix-views/s"
@@ -53,17 +57,53 @@ def algorithmic_bytes(nv, nf, T, P, C, S, depth=False):
     return fwd, bwd
 
 
+def sphere_mesh(n=225, perturb=0.0, seed=0):
+    """UV sphere, n x n vertices (n=225: 50 625 vertices, 100 352 faces); radius 0.8 times a seeded
+    low-frequency perturbation."""
+    i = torch.arange(n, dtype=torch.float32)
+    theta = (i / (n - 1) * 3.14159265)[:, None].expand(n, n)
+    phi = (i / (n - 1) * 2 * 3.14159265)[None, :].expand(n, n)
+    r = torch.full((n, n), 0.8)
+    if perturb:
+        g = torch.Generator().manual_seed(seed)
+        for _ in range(6):
+            a, kt, kp, ph = (torch.rand(1, generator=g).item() for _ in range(4))
+            r = r * (1 + perturb * (a - 0.5) * torch.sin((1 + int(kt * 4)) * theta + 6.28 * ph) *
+                     torch.cos((1 + int(kp * 4)) * phi))
+    v = torch.stack((r * torch.sin(theta) * torch.cos(phi), r * torch.cos(theta), r * torch.sin(theta) * torch.sin(phi)), -1)
+    idx = (torch.arange(n - 1)[:, None] * n + torch.arange(n - 1)[None, :]).reshape(-1)
+    f = torch.cat((torch.stack((idx, idx + 1, idx + n), 1), torch.stack((idx + 1, idx + n + 1, idx + n), 1)), 0)
+    return v.reshape(-1, 3).contiguous(), f.to(torch.int32).contiguous()
+
+
+def random_triangle_mesh(nf=1000000, seed=0):
+    """nf independent triangles: centres U(-1,1)^3, corner offsets N(0, 0.01^2); faces = arange."""
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand((nf, 1, 3), generator=g) * 2 - 1
+    v = (c + torch.randn((nf, 3, 3), generator=g) * 0.01).reshape(-1, 3)
+    v = v - v.min(0).values[None]                       # load_obj-style normalisation (load_obj.py:157-161)
+    v = v / v.abs().max() * 2
+    v = v - v.max(0).values[None] / 2
+    return v.contiguous(), torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3)
+
+
 def make_inputs(w, seed, device, nr):
-    d = np.load(os.path.join(ROOT, "tests", "golden", "teapot.npz"))
     B, S = w["views"], w["S"]
     g = torch.Generator().manual_seed(seed)
     elev = torch.rand(B, generator=g) * 80. - 20.
     azim = torch.rand(B, generator=g) * 360.
     eye = nr.get_points_from_angles(torch.full((B,), 2.732), elev, azim)
-    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
-    vs = nr.perspective(nr.look_at(vw, eye)).contiguous()          # screen space [B,nv,3], CPU
-    faces = torch.from_numpy(d["faces"])
-    out = dict(vertices=vs, faces=faces, nv=vs.shape[1], nf=faces.shape[0], T=0)
+    mesh = w.get("mesh", "teapot")
+    if mesh == "teapot":
+        d = np.load(os.path.join(ROOT, "tests", "golden", "teapot.npz"))
+        v_world, faces = torch.from_numpy(d["vertices"]), torch.from_numpy(d["faces"])
+    elif mesh == "sphere":
+        v_world, faces = sphere_mesh(225, perturb=0.3, seed=0)
+    else:
+        v_world, faces = random_triangle_mesh(1000000, seed=0)
+    tdev = device if (mesh == "random1m" and str(device) != "cpu") else "cpu"   # 3M vertices x 16 views: transform on the GPU
+    vs = nr.perspective(nr.look_at(v_world.to(tdev)[None].expand(B, -1, -1), eye.to(tdev))).contiguous()
+    out = dict(vertices=vs, faces=faces, nv=vs.shape[1], nf=faces.shape[0], T=0, eye=eye, v_world=v_world)
     if w["mode"] in ("rgb", "rgba"):
         vt_np, ft_np, tex_np = nr.create_textures(faces.shape[0], w["ts"])
         gt = torch.Generator().manual_seed(0)
@@ -182,24 +222,44 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident arm: `value`
-    v_dev = inp["vertices"].to(dev).requires_grad_(True)
-    tex_dev = inp["textures"].to(dev).requires_grad_(True) if rgb else None
+    shared = bool(w.get("shared"))
+    if shared:
+        # ONE mesh parameter for all views of all ranks: world -> screen transform inside the step,
+        # squared-error loss against the unperturbed sphere, gradient summed over views and ranks
+        param = inp["v_world"][None].to(dev).requires_grad_(True)
+        eye_d = inp["eye"].to(dev)
+        tv, _ = sphere_mesh(225, 0.0)
+        with torch.no_grad():
+            target = fn(nr.perspective(nr.look_at(tv.to(dev)[None].expand(B, -1, -1), eye_d)), faces,
+                        nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
+        params = [param]
+
+        def step_fn():
+            vs = nr.perspective(nr.look_at(nr.parallel.share_across_views(param, B), eye_d))
+            images = fn(vs, faces, nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
+            ((images - target) ** 2).sum().backward()
+            return images
+    else:
+        v_dev = inp["vertices"].to(dev).requires_grad_(True)
+        tex_dev = inp["textures"].to(dev).requires_grad_(True) if rgb else None
+        params = [v_dev] + ([tex_dev] if rgb else [])
+
+        def step_fn():
+            return step(v_dev, tex_dev)
+
+    def eager_step():
+        for p_ in params:
+            p_.grad = None
+        return step_fn()
+
     for _ in range(max(args.warmup, 3)):
-        v_dev.grad = None
-        if rgb:
-            tex_dev.grad = None
-        step(v_dev, tex_dev)
+        eager_step()
     barrier()
     # the whole step (forward + backward, ~12 short launches) is captured once in a CUDA graph and
     # replayed: every replay does the full work on the device; --eager launches from Python instead
-    if args.eager:
-        def run_step():
-            v_dev.grad = None
-            if rgb:
-                tex_dev.grad = None
-            return step(v_dev, tex_dev)
-    else:
-        run_step = nr.capture_step(lambda: step(v_dev, tex_dev), params=[v_dev] + ([tex_dev] if rgb else []), warmup=2)
+    # (also used when the step contains an NCCL all-reduce)
+    use_graph = not args.eager and not (shared and world > 1)
+    run_step = nr.capture_step(step_fn, params=params, warmup=2) if use_graph else eager_step
     for _ in range(3):
         run_step()
     barrier()
@@ -229,10 +289,7 @@ def run_ours(args):
     # ---- per-kernel pass (same inputs, right after the timed region): roofline numbers
     L.nr_profile_enable(1)
     for _ in range(args.steps):
-        v_dev.grad = None
-        if rgb:
-            tex_dev.grad = None
-        step(v_dev, tex_dev)
+        eager_step()
     torch.cuda.synchronize(dev)
     L.nr_profile_enable(0)
     import ctypes
@@ -245,18 +302,16 @@ def run_ours(args):
                             if n != "memset") / args.steps
 
     # ---- end-to-end arm: host (pinned) inputs -> H2D -> fwd + bwd -> D2H of the results
-    v_host = inp["vertices"].pin_memory()
-    tex_host = inp["textures"].pin_memory() if rgb else None
-    gv_host = torch.empty_like(v_host).pin_memory()
+    hosts = [p_.detach().cpu().pin_memory() for p_ in params]
+    gv_host = torch.empty_like(hosts[0]).pin_memory()
     chk_host = torch.empty(1).pin_memory()
 
     def e2e_step():
         # host (pinned) -> device copies of this step's inputs, the step, device -> host of its results
-        v_dev.data.copy_(v_host, non_blocking=True)
-        if rgb:
-            tex_dev.data.copy_(tex_host, non_blocking=True)
+        for p_, h_ in zip(params, hosts):
+            p_.data.copy_(h_, non_blocking=True)
         images = run_step()
-        gv_host.copy_(v_dev.grad, non_blocking=True)
+        gv_host.copy_(params[0].grad, non_blocking=True)
         chk_host.copy_(images.sum().reshape(1), non_blocking=True)
 
     for _ in range(3):
@@ -273,7 +328,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = world * B * S * S / 1e6 / (ms_e2e / args.steps / 1e3)
-    h2d = v_host.numel() * 4 + (tex_host.numel() * 4 if rgb else 0)
+    h2d = sum(h_.numel() * 4 for h_ in hosts)
     d2h = gv_host.numel() * 4 + 4
 
     if rank != 0:
@@ -310,15 +365,15 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: teapot (1292 v / 2464 f), %d views per GPU, %dx%d, anti_aliasing=%s, %s%s"
-                               % (args.workload, B, S, S, w["aa"], w["mode"],
+        "config": {"workload": "%s: %s (%d v / %d f), %d views per GPU, %dx%d, anti_aliasing=%s, %s%s"
+                               % (args.workload, w.get("mesh", "teapot"), inp["nv"], inp["nf"], B, S, S, w["aa"], w["mode"],
                                   (", texture_size %d (T=%d texels/view)" % (w["ts"], inp["T"])) if rgb else ""),
                    "views_per_gpu": B, "global_views": B * world, "image_size": S, "parallelism": "dp%d" % world,
                    "l2": "per-step working set %.2f GB > 126 MB L2, no explicit flush" % (step_bytes / 1e9)},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(round(launches_per_step * args.steps)),
-        "launch_mode": "eager (python)" if args.eager else "cuda graph replay of the whole step",
+        "launch_mode": "cuda graph replay of the whole step" if use_graph else "eager (python)",
         "host_ms_per_step": round(host_ms, 4),
         "clocks": clocks,
         "roofline": roofline,

@@ -194,7 +194,7 @@ k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restri
 // list.  Lists that the scatter kernel happened to fill in face order only pay the sortedness check.
 // Lists of <= 64 ids are rank-sorted in registers by one warp (two ids per lane); longer ones by
 // the whole CTA with a bitonic network in shared memory.
-constexpr int SORT_WARPS = 4;
+constexpr int SORT_WARPS = 8;
 constexpr int SORT_WARP_MAX = 64;     // lists up to this length: one warp each
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,

@@ -4,9 +4,9 @@
 
 namespace nr {
 
-// Tile lists up to this many faces are sorted in shared memory by the raster kernel;
+// Tile lists up to this many faces are sorted in shared memory (k_sort_tiles);
 // longer ones by k_sort_long in global memory.
-constexpr int SMEM_SORT_CAP = 1024;
+constexpr int SMEM_SORT_CAP = 8192;
 
 // Brackets one launch with CUDA events while nr_profile_enable(1) is in force (nr_profile.cu).
 enum ProfSlot { PROF_MEMSET = 0, PROF_SETUP, PROF_SCAN, PROF_SCATTER, PROF_SORT_LONG, PROF_RASTER,

@@ -143,17 +143,28 @@ k_raster(const RasterArgs a) {
         int best = -1;
         float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
 
+        // software pipeline over the list: while group g is culled and evaluated, the records of
+        // group g+1 and the ids of group g+2 are already in flight
+        auto load_id = [&](int i) -> int { return i < n ? (overflow ? i : __ldg(list + i)) : -1; };
+        int fid_next = load_id(lane);
+        int fid_next2 = load_id(32 + lane);
+        float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0;
+        if (fid_next >= 0) {
+            const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid_next);
+            n0 = __ldg(rp); n1 = __ldg(rp + 1); n2 = __ldg(rp + 2);
+        }
         for (int g = 0; g < n; g += 32) {
-            // ---- one face per lane: load, cull against this warp's block, compact the survivors
+            // ---- one face per lane: cull against this warp's block, compact the survivors
+            const int fid = fid_next;
+            const float4 q0 = n0, q1 = n1, q2 = n2;
+            fid_next = fid_next2;
+            if (fid_next >= 0) {
+                const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid_next);
+                n0 = __ldg(rp); n1 = __ldg(rp + 1); n2 = __ldg(rp + 2);
+            }
+            fid_next2 = load_id(g + 64 + lane);
             bool hit = false;
-            int fid = -1;
-            float4 q0, q1, q2;
-            if (g + lane < n) {
-                fid = overflow ? g + lane : __ldg(list + g + lane);
-                const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid);
-                q0 = __ldg(rp);
-                q1 = __ldg(rp + 1);
-                q2 = __ldg(rp + 2);
+            if (fid >= 0) {
                 const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
                 hit = ((int)(bx & 0xffff) <= wx1) && ((int)(bx >> 16) >= wx0) && ((int)(by & 0xffff) <= wy1) &&
                       ((int)(by >> 16) >= wy0);

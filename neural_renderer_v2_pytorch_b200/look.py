@@ -3,21 +3,14 @@ Pure torch, differentiable, O(nv): it runs before the hot path and is not accele
 import torch
 import torch.nn.functional as F
 
-from .look_at import _camera_rotation
+from .look_at import _camera_rotation, _as_batch
 
 
 def look(vertices, viewpoints, direction=None, up=None):
     assert vertices.ndim == 3
     dev, B = vertices.device, vertices.shape[0]
-
-    def as_batch(v, default):
-        if v is None:
-            v = default
-        v = torch.as_tensor(v, dtype=torch.float32, device=dev)
-        return v[None].expand(B, 3) if v.ndim == 1 else v
-
-    eye = as_batch(viewpoints, None)
-    direction = as_batch(direction, [0., 0., 1.])
-    up = as_batch(up, [0., 1., 0.])
+    eye = _as_batch(viewpoints, None, B, dev)
+    direction = _as_batch(direction, [0., 0., 1.], B, dev)
+    up = _as_batch(up, [0., 1., 0.], B, dev)
     r = _camera_rotation(F.normalize(direction, dim=-1), up)
     return torch.matmul(vertices - eye[:, None, :], r.transpose(1, 2))
