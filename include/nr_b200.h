@@ -111,6 +111,9 @@ NR_API int nr_event_query(void *event); /* 1 complete, 0 not yet, -1 error */
 NR_API int nr_profile_enable(int on);
 NR_API int nr_profile_collect(float *ms, int32_t *launches);
 
+/* Bytes of zero-filled scratch the deterministic backward needs. */
+NR_API size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg);
+
 /* Bytes of scratch the forward needs for `pair_capacity` (tile, face) pairs. */
 NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity);
 
@@ -163,13 +166,18 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
  *   grad_vertices       [B, nv, 3]   out, ACCUMULATED into (caller zero-fills)
  *   grad_textures       [B, 3, H, W] out, accumulated, optional
  *   grad_vertices_textures [B, nvt, 2] out, accumulated, optional
+ *   deterministic_scratch  only with NR_DETERMINISTIC in cfg->flags: nr_deterministic_scratch_bytes(cfg)
+ *                       zero-filled bytes.  Contributions are then rounded once to 64-bit fixed point
+ *                       (x 2^32) and summed with integer atomics, so the gradients are bit-identical from
+ *                       run to run (float atomics depend on arrival order).  Valid while every |sum| < 2.1e9;
+ *                       absolute resolution 2.3e-10.
  */
 NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
                           const float *textures, const int32_t *face_index_map,
                           const float *images_internal, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
-                          float *grad_vertices_textures, void *stream);
+                          float *grad_vertices_textures, void *deterministic_scratch, void *stream);
 
 /*
  * Differentiation.backward (differentiation.py:13-36) on channels-last tensors, as the

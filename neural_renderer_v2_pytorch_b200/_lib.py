@@ -26,7 +26,7 @@ NR_DETERMINISTIC = 32
 # every symbol include/nr_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (
     "nr_abi_version", "nr_last_error", "nr_num_channels", "nr_event_create", "nr_event_destroy",
-    "nr_event_synchronize", "nr_event_query", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
+    "nr_event_synchronize", "nr_event_query", "nr_deterministic_scratch_bytes", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
     "nr_differentiation_backward", "nr_face_index_map_forward_safe", "nr_compute_weight_map",
     "nr_profile_enable", "nr_profile_collect",
 )
@@ -103,7 +103,9 @@ def lib():
     L.nr_rasterize_forward.argtypes = [ctypes.POINTER(RasterConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                        vp, vp, vp, ctypes.c_size_t, i64, vp, vp, vp]
     L.nr_rasterize_backward.restype = ctypes.c_int
-    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 13
+    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 14
+    L.nr_deterministic_scratch_bytes.restype = ctypes.c_size_t
+    L.nr_deterministic_scratch_bytes.argtypes = [ctypes.POINTER(RasterConfig)]
     L.nr_differentiation_backward.restype = ctypes.c_int
     L.nr_differentiation_backward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.nr_face_index_map_forward_safe.restype = ctypes.c_int

@@ -156,6 +156,14 @@ int nr_event_synchronize(void *event) {
     return e == cudaSuccess ? NR_OK : fail_cuda(e, "cudaEventSynchronize");
 }
 
+size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg) {
+    if (!cfg) return 0;
+    const size_t n = (size_t)cfg->batch * cfg->num_vertices * 3 +
+                     (size_t)cfg->batch * 3 * cfg->tex_height * cfg->tex_width +
+                     (size_t)cfg->batch * cfg->num_tex_vertices * 2;
+    return n * sizeof(long long);
+}
+
 size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
     if (!cfg) return 0;
     const int R = cfg->image_size * ((cfg->flags & NR_ANTI_ALIASING) ? 2 : 1);
@@ -269,7 +277,7 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
                           const float *textures, const int32_t *face_index_map,
                           const float *images_internal, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
-                          float *grad_vertices_textures, void *stream_) {
+                          float *grad_vertices_textures, void *deterministic_scratch, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
     if (!vertices || !face_index_map || !images_internal || !grad_images || !grad_vertices)
@@ -291,6 +299,20 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
     a.grad_verts = grad_vertices;
     a.grad_tex = grad_textures;
     a.grad_vt = grad_vertices_textures;
+    a.det_verts = a.det_tex = a.det_vt = nullptr;
+    a.det_scale = 4294967296.f;     // 2^32: resolution 2.3e-10, |sum| < 2.1e9
+    if (cfg->flags & NR_DETERMINISTIC) {
+        if (!deterministic_scratch || ((uintptr_t)deterministic_scratch & 7))
+            return fail(NR_ERR_INVALID_ARGUMENT, "NR_DETERMINISTIC needs deterministic_scratch (8-byte aligned, zero-filled)");
+        long long *p = (long long *)deterministic_scratch;
+        a.det_verts = p;
+        p += (size_t)cfg->batch * cfg->num_vertices * 3;
+        if (grad_textures) {
+            a.det_tex = p;
+            p += (size_t)cfg->batch * 3 * cfg->tex_height * cfg->tex_width;
+        }
+        if (grad_vertices_textures) a.det_vt = p;
+    }
     a.B = cfg->batch;
     a.nv = cfg->num_vertices;
     a.nf = cfg->num_faces;

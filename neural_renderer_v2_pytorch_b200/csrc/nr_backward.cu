@@ -170,8 +170,22 @@ __device__ __forceinline__ bool run_reduce(int key, bool valid, float (&v)[N], i
 // C = channel count at compile time (0: read it from the arguments).
 // Persistent over the forward's list of non-empty 16x16 tiles (grid-stride); a warp owns two
 // 16-pixel row segments of the tile, so the pixels of one face form runs in lane order.
-template <int CT, bool NEED_UV>
-__global__ void __launch_bounds__(TILE_THREADS)
+// Accumulate one contribution.  Float atomics (default) commute only up to rounding, so the result
+// depends on arrival order; in deterministic mode the value is rounded ONCE to 64-bit fixed point
+// (value * 2^k) and added with integer atomics, which are exactly associative: the sum is bit-identical
+// from run to run whatever the order.  The warp-level run sums in front of it have a fixed order.
+template <bool DET>
+__device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, size_t idx, float v, float scale) {
+    if (DET) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(dst_i + idx),
+                  (unsigned long long)__double2ll_rn((double)v * (double)scale));
+    } else {
+        atomicAdd(dst_f + idx, v);
+    }
+}
+
+template <int CT, bool NEED_UV, bool DET>
+__global__ void __launch_bounds__(TILE_THREADS, 3)
 k_backward(const BackwardArgs a) {
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
     const int R = a.R, S = a.S, C = CT ? CT : a.C;
@@ -299,11 +313,11 @@ k_backward(const BackwardArgs a) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) tg[t * 3 + c] = tw[t] * g[c];
                 if (NEED_UV) {
-                    float *gvt = a.grad_vt + (size_t)b * a.nvt * 2;
+                    const size_t o = (size_t)b * a.nvt * 2;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        if (gu[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k], gu[k]);
-                        if (gv[k] != 0.f) atomicAdd(gvt + 2 * (size_t)tvid[k] + 1, gv[k]);
+                        if (gu[k] != 0.f) accumulate<DET>(a.grad_vt, a.det_vt, o + 2 * (size_t)tvid[k], gu[k], a.det_scale);
+                        if (gv[k] != 0.f) accumulate<DET>(a.grad_vt, a.det_vt, o + 2 * (size_t)tvid[k] + 1, gv[k], a.det_scale);
                     }
                 }
             }
@@ -336,13 +350,13 @@ k_backward(const BackwardArgs a) {
         if (__ballot_sync(0xffffffffu, nz) != 0u) {
             const bool tail = run_reduce<9>(f, fg, vg, lane);
             if (tail && fg) {
-                float *gvb = a.grad_verts + (size_t)b * a.nv * 3;
+                const size_t o = (size_t)b * a.nv * 3;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    float *dst = gvb + 3 * (size_t)vid[k];
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (vg[3 * k + c] != 0.f) atomicAdd(dst + c, vg[3 * k + c]);
+                        if (vg[3 * k + c] != 0.f)
+                            accumulate<DET>(a.grad_verts, a.det_verts, o + 3 * (size_t)vid[k] + c, vg[3 * k + c], a.det_scale);
                 }
             }
         }
@@ -353,19 +367,25 @@ k_backward(const BackwardArgs a) {
         if (__ballot_sync(0xffffffffu, has) != 0u) {
             const bool tail = run_reduce<12>(cell, has, tg, lane);
             if (tail && has) {
-                float *gtb = a.grad_tex + (size_t)b * 3 * a.H * a.W;
-                const size_t T = (size_t)a.H * a.W;
+                const size_t T = (size_t)a.H * a.W, o = (size_t)b * 3 * T;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     if (tap[t] < 0) continue;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (tg[t * 3 + c] != 0.f) atomicAdd(gtb + c * T + tap[t], tg[t * 3 + c]);
+                        if (tg[t * 3 + c] != 0.f)
+                            accumulate<DET>(a.grad_tex, a.det_tex, o + c * T + tap[t], tg[t * 3 + c], a.det_scale);
                 }
             }
         }
     }
     }   // tiles
+}
+
+__global__ void __launch_bounds__(256)
+k_fixed_to_float(const long long *__restrict__ src, float *__restrict__ dst, size_t n, float inv_scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += (float)((double)src[i] * (double)inv_scale);
 }
 
 // Differentiation.backward on channels-last tensors (the public differentiation() op).
@@ -393,16 +413,29 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
     dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
-    if (a.grad_vt) {
-        k_backward<0, true><<<grid, block, 0, stream>>>(a);
+    if (a.det_verts) {
+        if (a.grad_vt) k_backward<0, true, true><<<grid, block, 0, stream>>>(a);
+        else k_backward<0, false, true><<<grid, block, 0, stream>>>(a);
+    } else if (a.grad_vt) {
+        k_backward<0, true, false><<<grid, block, 0, stream>>>(a);
     } else {
         switch (a.C) {
-            case 1: k_backward<1, false><<<grid, block, 0, stream>>>(a); break;
-            case 3: k_backward<3, false><<<grid, block, 0, stream>>>(a); break;
-            case 4: k_backward<4, false><<<grid, block, 0, stream>>>(a); break;
-            default: k_backward<0, false><<<grid, block, 0, stream>>>(a); break;
+            case 1: k_backward<1, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 3: k_backward<3, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 4: k_backward<4, false, false><<<grid, block, 0, stream>>>(a); break;
+            default: k_backward<0, false, false><<<grid, block, 0, stream>>>(a); break;
         }
     }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !a.det_verts) return e;
+    // fixed point -> float, added onto the caller's (zero-filled) gradient tensors
+    const float inv = 1.f / a.det_scale;
+    auto conv = [&](const long long *src, float *dst, size_t n) {
+        if (src && dst && n) k_fixed_to_float<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n, inv);
+    };
+    conv(a.det_verts, a.grad_verts, (size_t)a.B * a.nv * 3);
+    conv(a.det_tex, a.grad_tex, (size_t)a.B * 3 * a.H * a.W);
+    conv(a.det_vt, a.grad_vt, (size_t)a.B * a.nvt * 2);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,10 @@ struct BackwardArgs {
     const int32_t *tile_list;   // non-empty tiles of the forward, or null (all tiles)
     int sm_count;
     float *grad_verts, *grad_tex, *grad_vt;
+    // deterministic mode: 64-bit fixed-point accumulators (same shapes as the three gradients,
+    // laid out back to back) and the power-of-two scale; null = float atomics
+    long long *det_verts, *det_tex, *det_vt;
+    float det_scale;
     int B, nv, nf, R, S, ntx, C, flags, nvt, H, W;
     float eps;
 };

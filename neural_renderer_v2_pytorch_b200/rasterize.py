@@ -20,6 +20,10 @@ from .rasterize_param import RasterizeParam, RasterizeHyperparam
 
 DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
 
+# Deterministic backward (bit-identical gradients from run to run): set to True, or per call through
+# RasterizeHyperparam(...).deterministic = True.  Costs one int64 scratch buffer per backward.
+DETERMINISTIC = False
+
 # test hook: force the (tile, face) pair capacity (e.g. 0) to exercise the device-side overflow path
 FORCE_PAIR_CAPACITY = None
 
@@ -107,7 +111,8 @@ def _flags_of(hp):
             (_lib.NR_DRAW_SILHOUETTES if hp.draw_silhouettes else 0) |
             (_lib.NR_DRAW_DEPTH if hp.draw_depth else 0) |
             (_lib.NR_DRAW_BACKSIDE if hp.draw_backside else 0) |
-            (_lib.NR_ANTI_ALIASING if hp.anti_aliasing else 0))
+            (_lib.NR_ANTI_ALIASING if hp.anti_aliasing else 0) |
+            (_lib.NR_DETERMINISTIC if (DETERMINISTIC or getattr(hp, "deterministic", False)) else 0))
 
 
 def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
@@ -214,9 +219,12 @@ class _Rasterize(torch.autograd.Function):
             gv = torch.zeros_like(v)
             gvt = torch.zeros_like(vt) if (need_vt and vt is not None) else None
             gtex = torch.zeros_like(tex) if (need_tex and tex is not None) else None
+            scratch = None
+            if cfg.flags & _lib.NR_DETERMINISTIC:
+                scratch = torch.zeros(L.nr_deterministic_scratch_bytes(ctypes.byref(cfg)) // 8, dtype=torch.int64, device=dev)
             rc = L.nr_rasterize_backward(ctypes.byref(cfg), _ptr(v), _ptr(faces), _ptr(vt), _ptr(ft),
                                          _ptr(tex), _ptr(fim), _ptr(internal), _ptr(tile_list), _ptr(g), _ptr(gv),
-                                         _ptr(gtex), _ptr(gvt), ctypes.c_void_p(stream))
+                                         _ptr(gtex), _ptr(gvt), _ptr(scratch), ctypes.c_void_p(stream))
             _lib.check(rc, "nr_rasterize_backward")
         return (gv if need_v else None), gvt, gtex, None, None, None
 

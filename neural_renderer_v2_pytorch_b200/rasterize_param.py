@@ -14,6 +14,8 @@ class RasterizeHyperparam:
         self.draw_rgb = draw_rgb
         self.draw_silhouettes = draw_silhouettes
         self.draw_depth = draw_depth
+        # not in the reference: bit-reproducible gradients (fixed-point accumulation, see nr_b200.h)
+        self.deterministic = False
 
 
 class RasterizeParam:

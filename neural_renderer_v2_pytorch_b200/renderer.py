@@ -30,6 +30,9 @@ class Renderer(object):
         self.near = 0.1
         self.far = 100
 
+        # not in the reference: bit-reproducible gradients (see RasterizeHyperparam.deterministic)
+        self.deterministic = False
+
     def transform_vertices(self, vertices, lights=None):
         """World -> screen space (renderer.py:24-35)."""
         if self.camera_mode == 'look_at':
@@ -41,8 +44,10 @@ class Renderer(object):
         return vertices
 
     def _hyperparams(self):
-        return RasterizeHyperparam(image_size=self.image_size, near=self.near, far=self.far,
-                                   anti_aliasing=self.anti_aliasing, draw_backside=self.draw_backside)
+        hp = RasterizeHyperparam(image_size=self.image_size, near=self.near, far=self.far,
+                                 anti_aliasing=self.anti_aliasing, draw_backside=self.draw_backside)
+        hp.deterministic = self.deterministic
+        return hp
 
     def render_silhouettes(self, vertices, faces, backgrounds=None):
         """[B,nv,3], [nf,3] -> [B,S,S] (renderer.py:37-46)."""

@@ -235,6 +235,33 @@ def test_pair_list_overflow_falls_back_on_device(nr):
     assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
 
 
+def test_deterministic_mode_is_bit_reproducible(nr):
+    """hyperparams.deterministic: gradients bit-identical from run to run, and still within the
+    tolerance of the reference's gradients."""
+    d = np.load(os.path.join(GOLDEN, "case_rgba_64.npz"))
+    dev = "cuda:0"
+
+    def run():
+        hp = nr.RasterizeHyperparam(image_size=int(d["image_size"]), anti_aliasing=False)
+        hp.deterministic = True
+        v = torch.from_numpy(d["vertices"]).to(dev).requires_grad_(True)
+        tex = torch.from_numpy(d["textures"]).to(dev).requires_grad_(True)
+        vt = torch.from_numpy(d["vertices_textures"]).to(dev).requires_grad_(True)
+        p = nr.RasterizeParam(vertices_textures=vt, faces_textures=torch.from_numpy(d["faces_textures"]).to(dev), textures=tex)
+        img = nr.rasterize_rgba(v, torch.from_numpy(d["faces"]).to(dev), p, hp)
+        (img * torch.from_numpy(d["grad_images"]).to(dev)).sum().backward()
+        return v.grad.clone(), tex.grad.clone(), vt.grad.clone()
+
+    first = run()
+    for _ in range(5):
+        again = run()
+        for a, b in zip(first, again):
+            assert torch.equal(a, b), "deterministic mode produced different bits"
+    grad_close(first[0].cpu().numpy(), d["grad_vertices"], "grad_vertices")
+    grad_close(first[1].cpu().numpy(), d["grad_textures"], "grad_textures")
+    grad_close(first[2].cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
+
+
 def test_teapot_views(nr):
     d = np.load(os.path.join(GOLDEN, "teapot.npz"))
     B = 4
