@@ -185,7 +185,7 @@ __device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, size_
 }
 
 template <int CT, bool NEED_UV, bool DET>
-__global__ void __launch_bounds__(TILE_THREADS, 3)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 k_backward(const BackwardArgs a) {
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
     const int R = a.R, S = a.S, C = CT ? CT : a.C;

@@ -192,75 +192,92 @@ k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restri
 
 // Ascending in-place sort of every tile list of up to SMEM_SORT_CAP faces, grid-stride over the work
 // list.  Lists that the scatter kernel happened to fill in face order only pay the sortedness check.
-// Lists of <= 64 ids are rank-sorted in registers by one warp (two ids per lane); longer ones by
+// Lists of <= 128 ids are rank-sorted in registers by one warp (four ids per lane); longer ones by
 // the whole CTA with a bitonic network in shared memory.
 constexpr int SORT_WARPS = 8;
-constexpr int SORT_WARP_MAX = 64;     // lists up to this length: one warp each
+constexpr int SORT_PER_LANE = 4;
+constexpr int SORT_WARP_MAX = 32 * SORT_PER_LANE;     // lists up to this length: one warp each
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
              const BinHeader *__restrict__ hdr) {
     __shared__ int s_ids[SMEM_SORT_CAP];
+    __shared__ int s_long[SORT_WARPS * 32];
+    __shared__ int s_nlong;
     if (hdr->overflow) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int count = tile_list[0];
     const int4 *entries = reinterpret_cast<const int4 *>(tile_list + TILE_LIST_HDR);
 
-    // ---- pass A: short lists, one warp per list
+    // ---- pass A: lists of up to 128 ids, one warp per list, ids held in registers
+    // (position p of the list lives in register p / 32 of lane p % 32)
     for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
         const int4 e = entries[w];
         const int n = e.w;
         if (n < 2 || n > SORT_WARP_MAX) continue;
         int32_t *a = pairs + e.z;
-        // two ids per lane: positions lane and lane + 32
-        const int v0 = lane < n ? a[lane] : 0x7fffffff;
-        const int v1 = lane + 32 < n ? a[lane + 32] : 0x7fffffff;
-        const int nx0 = __shfl_down_sync(0xffffffffu, v0, 1), nx1 = __shfl_down_sync(0xffffffffu, v1, 1);
-        const int first1 = __shfl_sync(0xffffffffu, v1, 0);
-        const bool bad = (lane < 31 ? v0 > nx0 : v0 > first1) || (lane < 31 && v1 > nx1);
-        if (__ballot_sync(0xffffffffu, bad) == 0u) continue;
-        int r0 = 0, r1 = 0;
+        int v[SORT_PER_LANE];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int x = __shfl_sync(0xffffffffu, v0, j), y = __shfl_sync(0xffffffffu, v1, j);
-            r0 += (x < v0) + (y < v0);
-            r1 += (x < v1) + (y < v1);
+        for (int k = 0; k < SORT_PER_LANE; ++k) v[k] = (k * 32 + lane < n) ? a[k * 32 + lane] : 0x7fffffff;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < SORT_PER_LANE; ++k) {
+            const int nxt = __shfl_down_sync(0xffffffffu, v[k], 1);
+            const int wrap = (k + 1 < SORT_PER_LANE) ? __shfl_sync(0xffffffffu, v[k + 1 < SORT_PER_LANE ? k + 1 : k], 0) : 0x7fffffff;
+            bad |= v[k] > (lane < 31 ? nxt : wrap);
+        }
+        if (__ballot_sync(0xffffffffu, bad) == 0u) continue;
+        int r[SORT_PER_LANE];
+#pragma unroll
+        for (int k = 0; k < SORT_PER_LANE; ++k) r[k] = 0;
+        const int groups = (n + 31) >> 5;
+#pragma unroll
+        for (int kk = 0; kk < SORT_PER_LANE; ++kk) {
+            if (kk < groups) {
+                for (int j = 0; j < 32; ++j) {
+                    const int x = __shfl_sync(0xffffffffu, v[kk], j);
+#pragma unroll
+                    for (int k = 0; k < SORT_PER_LANE; ++k) r[k] += (x < v[k]);
+                }
+            }
         }
         __syncwarp();
-        if (lane < n) a[r0] = v0;          // ids are unique inside one list
-        if (lane + 32 < n) a[r1] = v1;
+#pragma unroll
+        for (int k = 0; k < SORT_PER_LANE; ++k)
+            if (k * 32 + lane < n) a[r[k]] = v[k];          // ids are unique inside one list
     }
 
-    // ---- pass B: longer lists, the whole CTA per list (same-direction bitonic network over a
-    // virtual power-of-two length: indices >= n behave as +inf and never move)
-    for (int w = blockIdx.x; w < count; w += gridDim.x) {
-        const int4 e = entries[w];
-        const int n = e.w;
-        if (n <= SORT_WARP_MAX || n > SMEM_SORT_CAP) continue;      // CTA-uniform
-        int32_t *a = pairs + e.z;
-        int unsorted = 0;
-        for (int i = tid; i < n; i += blockDim.x) s_ids[i] = a[i];
+    // ---- pass B: longer lists, the whole CTA per list.  First every thread looks at one entry
+    // of this CTA's share (independent loads), the long ones are compacted, then sorted one by one
+    // with a same-direction bitonic network over a virtual power-of-two length (indices >= n behave
+    // as +inf and never move).
+    // (entry w belongs to CTA w % gridDim.x, so neighbouring, similarly long lists spread over CTAs)
+    for (int base = 0; base * (int)gridDim.x + (int)blockIdx.x < count; base += blockDim.x) {
+        if (tid == 0) s_nlong = 0;
         __syncthreads();
-        for (int i = tid; i + 1 < n; i += blockDim.x) unsorted |= (s_ids[i] > s_ids[i + 1]);
-        if (__syncthreads_or(unsorted)) {
-            int lg = 7;
-            while ((1 << lg) < n) ++lg;
-            const int half = 1 << (lg - 1);
-            for (int kk = 1; kk <= lg; ++kk) {
-                const int k = 1 << kk;
-                for (int i = tid; i < half; i += blockDim.x) {
-                    const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
-                    const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
-                    if (hi < n && s_ids[lo] > s_ids[hi]) {
-                        const int t = s_ids[lo];
-                        s_ids[lo] = s_ids[hi];
-                        s_ids[hi] = t;
-                    }
-                }
-                __syncthreads();
-                for (int jj = kk - 2; jj >= 0; --jj) {
-                    const int j = 1 << jj;
+        const int w = (base + tid) * (int)gridDim.x + (int)blockIdx.x;
+        if (w < count) {
+            const int n = entries[w].w;
+            if (n > SORT_WARP_MAX && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
+        }
+        __syncthreads();
+        const int nlong = s_nlong;
+        for (int li = 0; li < nlong; ++li) {
+            const int4 e = entries[s_long[li]];
+            const int n = e.w;
+            int32_t *a = pairs + e.z;
+            int unsorted = 0;
+            for (int i = tid; i < n; i += blockDim.x) s_ids[i] = a[i];
+            __syncthreads();
+            for (int i = tid; i + 1 < n; i += blockDim.x) unsorted |= (s_ids[i] > s_ids[i + 1]);
+            if (__syncthreads_or(unsorted)) {
+                int lg = 8;
+                while ((1 << lg) < n) ++lg;
+                const int half = 1 << (lg - 1);
+                for (int kk = 1; kk <= lg; ++kk) {
+                    const int k = 1 << kk;
                     for (int i = tid; i < half; i += blockDim.x) {
-                        const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
+                        const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
+                        const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
                         if (hi < n && s_ids[lo] > s_ids[hi]) {
                             const int t = s_ids[lo];
                             s_ids[lo] = s_ids[hi];
@@ -268,9 +285,22 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
                         }
                     }
                     __syncthreads();
+                    for (int jj = kk - 2; jj >= 0; --jj) {
+                        const int j = 1 << jj;
+                        for (int i = tid; i < half; i += blockDim.x) {
+                            const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
+                            if (hi < n && s_ids[lo] > s_ids[hi]) {
+                                const int t = s_ids[lo];
+                                s_ids[lo] = s_ids[hi];
+                                s_ids[hi] = t;
+                            }
+                        }
+                        __syncthreads();
+                    }
                 }
+                for (int i = tid; i < n; i += blockDim.x) a[i] = s_ids[i];
             }
-            for (int i = tid; i < n; i += blockDim.x) a[i] = s_ids[i];
+            __syncthreads();
         }
         __syncthreads();
     }

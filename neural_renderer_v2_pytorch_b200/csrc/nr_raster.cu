@@ -91,7 +91,7 @@ __device__ __forceinline__ bool block_outside_face(float x0, float y0, float x1,
 // Background pixels were pre-filled by launch_raster, so only foreground pixels are written.
 constexpr int RASTER_WARPS = TILE_THREADS / 32;
 
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 k_raster(const RasterArgs a) {
     __shared__ float4 s_rec[RASTER_WARPS][32][4];
     __shared__ uint2 s_bb[RASTER_WARPS][32];
