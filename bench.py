@@ -33,6 +33,8 @@ WORKLOADS = {
     "cfg2s": dict(views=64, S=512, aa=False, mode="silhouettes", ts=0, mesh="teapot"),
     "cfg1": dict(views=1, S=256, aa=True, mode="rgba", ts=16, mesh="teapot"),
     "cfg5": dict(views=32, S=512, aa=True, mode="rgb", ts=4, mesh="teapot"),
+    # config 2 through the Renderer facade: world-space vertices -> camera transform -> rasterize
+    "cfg2r": dict(views=64, S=512, aa=False, mode="rgba", ts=4, mesh="teapot", renderer=True),
     # multi-view optimisation of ONE shared 100k-face mesh: gradient all-reduce across ranks
     "cfg3": dict(views=8, S=512, aa=False, mode="silhouettes", ts=0, mesh="sphere", shared=True),
     # 1M independent ~5 px triangles: stresses binning, list sorting and z-test contention
@@ -238,6 +240,19 @@ def run_ours(args):
             vs = nr.perspective(nr.look_at(nr.parallel.share_across_views(param, B), eye_d))
             images = fn(vs, faces, nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
             ((images - target) ** 2).sum().backward()
+            return images
+    elif w.get("renderer"):
+        # the call a user of the reference makes: Renderer.render(world vertices, ...)
+        v_dev = inp["v_world"][None].repeat(B, 1, 1).to(dev).requires_grad_(True)
+        tex_dev = inp["textures"].to(dev).requires_grad_(True)
+        params = [v_dev, tex_dev]
+        rend = nr.Renderer()
+        rend.image_size, rend.anti_aliasing, rend.viewpoints = S, w["aa"], inp["eye"].to(dev)
+        rend.fused_camera = not args.unfused_camera
+
+        def step_fn():
+            images = rend.render(v_dev, faces, vt, ft, tex_dev)
+            images.backward(G)
             return images
     else:
         v_dev = inp["vertices"].to(dev).requires_grad_(True)
@@ -503,6 +518,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused-camera", action="store_true", help="cfg2r: camera transform as torch ops")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

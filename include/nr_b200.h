@@ -189,6 +189,21 @@ NR_API int nr_differentiation_backward(const float *images, const float *grad_ou
                                 int32_t channels, void *stream);
 
 /*
+ * Fused camera transform (look_at.py:28-42 + perspective.py:9-17): out = persp(R (v - eye)).
+ *   vertices [B, nv, 3] world space, rotation [B, 3, 3] (rows = camera x, y, z axes), eye [B, 3]
+ *   out [B, nv, 3] screen space; perspective != 0 divides x and y by z and by width = tan(angle).
+ * Backward: grad_vertices [B, nv, 3] is written; partial [B, nr_camera_partial_blocks(nv), 12] receives
+ * per-block sums of d loss / d rotation (9, row-major) and d loss / d eye (3) - sum them over dim 1.
+ */
+NR_API int nr_camera_partial_blocks(int32_t num_vertices);
+NR_API int nr_camera_forward(const float *vertices, const float *rotation, const float *eye, float *out,
+                             int32_t batch, int32_t num_vertices, int32_t perspective, float width,
+                             void *stream);
+NR_API int nr_camera_backward(const float *vertices, const float *rotation, const float *eye,
+                              const float *grad_out, float *grad_vertices, float *partial, int32_t batch,
+                              int32_t num_vertices, int32_t perspective, float width, void *stream);
+
+/*
  * Same operator as face_index_map_forward_safe (rasterize_cuda.cpp:55-65):
  *   faces [B, nf, 3, 3], face_index [B*S*S] written in place (pre-fill not required).
  * `eps` is accepted and unused, like in the reference kernel.  Scratch is taken from a

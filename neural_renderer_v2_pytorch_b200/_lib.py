@@ -28,7 +28,8 @@ SYMBOLS = (
     "nr_abi_version", "nr_last_error", "nr_num_channels", "nr_event_create", "nr_event_destroy",
     "nr_event_synchronize", "nr_event_query", "nr_deterministic_scratch_bytes", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
     "nr_differentiation_backward", "nr_face_index_map_forward_safe", "nr_compute_weight_map",
-    "nr_profile_enable", "nr_profile_collect",
+    "nr_profile_enable", "nr_profile_collect", "nr_camera_partial_blocks", "nr_camera_forward",
+    "nr_camera_backward",
 )
 NR_PROF_SLOTS = 9
 PROF_SLOT_NAMES = ("memset", "setup_count", "scan_tiles", "scatter", "sort_long", "raster", "backward",
@@ -116,6 +117,12 @@ def lib():
     L.nr_profile_enable.argtypes = [ctypes.c_int]
     L.nr_profile_collect.restype = ctypes.c_int
     L.nr_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+    L.nr_camera_partial_blocks.restype = ctypes.c_int
+    L.nr_camera_partial_blocks.argtypes = [i32]
+    L.nr_camera_forward.restype = ctypes.c_int
+    L.nr_camera_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    L.nr_camera_backward.restype = ctypes.c_int
+    L.nr_camera_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     if L.nr_abi_version() != 1:
         raise RuntimeError("libnr_b200.so ABI version mismatch")
     _lib = L

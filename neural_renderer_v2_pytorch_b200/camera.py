@@ -1,0 +1,79 @@
+"""Fused camera transform: world-space vertices + per-view camera -> screen space in ONE kernel,
+with ONE backward kernel.
+
+Replaces, inside ``Renderer.transform_vertices`` (reference ``renderer.py:24-35``), the chain
+``look_at`` / ``look`` (``look_at.py:28-42``, ``look.py:27-40``) -> ``perspective``
+(``perspective.py:9-17``): ~10 elementwise / bmm launches forward and ~15 backward over [B,nv,3]
+tensors.  The 3x3 camera rotation is still built with torch ops on [B,3] tensors (so gradients to
+``viewpoints`` keep flowing through normalize / cross exactly as in the reference); only the O(nv)
+part is fused.  The standalone ``look_at`` / ``look`` / ``perspective`` functions remain plain torch.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .look_at import _as_batch, _camera_rotation
+from .perspective import _PI_REF
+
+
+class _CameraTransform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vertices, rotation, eye, perspective, width):
+        v = vertices.detach().to(torch.float32).contiguous()
+        r = rotation.detach().to(torch.float32).contiguous()
+        e = eye.detach().to(torch.float32).contiguous()
+        B, nv = v.shape[:2]
+        out = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            rc = _lib.lib().nr_camera_forward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
+                                              ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, nv,
+                                              int(perspective), float(width), ctypes.c_void_p(stream))
+        _lib.check(rc, "nr_camera_forward")
+        ctx.save_for_backward(v, r, e)
+        ctx.perspective, ctx.width = int(perspective), float(width)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        v, r, e = ctx.saved_tensors
+        g = grad_out.detach().to(torch.float32).contiguous()
+        B, nv = v.shape[:2]
+        L = _lib.lib()
+        gv = torch.empty_like(v)
+        partial = torch.empty((B, L.nr_camera_partial_blocks(nv), 12), dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            rc = L.nr_camera_backward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
+                                      ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(g.data_ptr()),
+                                      ctypes.c_void_p(gv.data_ptr()), ctypes.c_void_p(partial.data_ptr()), B, nv,
+                                      ctx.perspective, ctx.width, ctypes.c_void_p(stream))
+        _lib.check(rc, "nr_camera_backward")
+        red = partial.sum(1)                               # fixed-order reduction of the per-block sums
+        return gv, red[:, :9].reshape(B, 3, 3), red[:, 9:], None, None
+
+
+def transform_vertices(vertices, viewpoints, camera_mode="look_at", camera_direction=None, perspective=True,
+                       viewing_angle=30., at=None, up=None):
+    """Screen-space vertices [B,nv,3] of ``vertices`` [B,nv,3] (CUDA) seen from ``viewpoints``."""
+    assert vertices.ndim == 3
+    dev, B = vertices.device, vertices.shape[0]
+    eye = _as_batch(viewpoints, None, B, dev)
+    up = _as_batch(up, [0., 1., 0.], B, dev)
+    if camera_mode == "look_at":
+        z_axis = F.normalize(_as_batch(at, [0., 0., 0.], B, dev) - eye, dim=-1)
+    elif camera_mode == "look":
+        z_axis = F.normalize(_as_batch(camera_direction, [0., 0., 1.], B, dev), dim=-1)
+    else:                                                  # no viewpoint transformation (renderer.py:26-29)
+        z_axis = None
+    if z_axis is None:
+        rot = torch.eye(3, device=dev).expand(B, 3, 3)
+        eye = torch.zeros((B, 3), device=dev)
+    else:
+        rot = _camera_rotation(z_axis, up)
+    if torch.is_tensor(viewing_angle):
+        raise TypeError("the fused transform takes a scalar viewing angle; use look_at + perspective for a tensor")
+    width = float(torch.tan(torch.tensor(float(viewing_angle), dtype=torch.float32) / 180. * _PI_REF))
+    return _CameraTransform.apply(vertices, rot, eye.expand(B, 3), bool(perspective), width)

@@ -1,0 +1,126 @@
+// nr_camera.cu -- fused camera transform.
+//
+// World-space vertices + per-view camera -> screen-space vertices in one kernel, and its backward in
+// one kernel, instead of the ~10 + ~15 elementwise / bmm launches of
+//   look_at   (neural_renderer_torch/look_at.py:28-42):  (v - eye) @ R^T
+//   perspective (neural_renderer_torch/perspective.py:9-17): x / z / width, y / z / width, z
+// The 3x3 rotation R (rows = camera x, y, z axes) is built by the caller from the eye / at / up
+// vectors with torch ops on [B,3] tensors, so its own backward (normalize, cross) stays in autograd.
+#include "../../include/nr_b200.h"
+#include "nr_kernels.h"
+
+namespace nr {
+
+constexpr int CAM_THREADS = 256;
+
+__global__ void __launch_bounds__(CAM_THREADS)
+k_camera_forward(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
+                 float *__restrict__ out, int nv, int perspective, float width) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const float *R = rot + (size_t)b * 9, *E = eye + (size_t)b * 3;
+    const float *v = verts + ((size_t)b * nv + i) * 3;
+    const float d0 = __fsub_rn(v[0], E[0]), d1 = __fsub_rn(v[1], E[1]), d2 = __fsub_rn(v[2], E[2]);
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = __fmaf_rn(R[3 * r + 2], d2, __fmaf_rn(R[3 * r + 1], d1, __fmul_rn(R[3 * r], d0)));
+    float *o = out + ((size_t)b * nv + i) * 3;
+    if (perspective) {
+        o[0] = __fdiv_rn(__fdiv_rn(c[0], c[2]), width);
+        o[1] = __fdiv_rn(__fdiv_rn(c[1], c[2]), width);
+    } else {
+        o[0] = c[0];
+        o[1] = c[1];
+    }
+    o[2] = c[2];
+}
+
+// grad_verts [B,nv,3] written; per-CTA partial sums of d loss / d R (9) and d loss / d eye (3) written
+// to partial [B, gridDim.x, 12] (summed by the caller in a fixed order: deterministic).
+__global__ void __launch_bounds__(CAM_THREADS)
+k_camera_backward(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
+                  const float *__restrict__ gout, float *__restrict__ gverts, float *__restrict__ partial, int nv,
+                  int perspective, float width) {
+    __shared__ float s_red[CAM_THREADS / 32][12];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float *R = rot + (size_t)b * 9, *E = eye + (size_t)b * 3;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+    if (i < nv) {
+        const float *v = verts + ((size_t)b * nv + i) * 3;
+        const float *g = gout + ((size_t)b * nv + i) * 3;
+        const float d[3] = {v[0] - E[0], v[1] - E[1], v[2] - E[2]};
+        float gc[3] = {g[0], g[1], g[2]};
+        if (perspective) {
+            float c[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) c[r] = R[3 * r] * d[0] + R[3 * r + 1] * d[1] + R[3 * r + 2] * d[2];
+            const float iz = 1.f / c[2], izw = iz / width;
+            gc[2] = g[2] - (g[0] * c[0] + g[1] * c[1]) * iz * izw;
+            gc[0] = g[0] * izw;
+            gc[1] = g[1] * izw;
+        }
+        float gd[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gd[j] = R[j] * gc[0] + R[3 + j] * gc[1] + R[6 + j] * gc[2];
+        float *gv = gverts + ((size_t)b * nv + i) * 3;
+        gv[0] = gd[0];
+        gv[1] = gd[1];
+        gv[2] = gd[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[3 * r + j] = gc[r] * d[j];
+        acc[9] = -gd[0];
+        acc[10] = -gd[1];
+        acc[11] = -gd[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        float x = acc[k];
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[wid][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float x = 0.f;
+        for (int w = 0; w < CAM_THREADS / 32; ++w) x += s_red[w][threadIdx.x];
+        partial[((size_t)b * gridDim.x + blockIdx.x) * 12 + threadIdx.x] = x;
+    }
+}
+
+}  // namespace nr
+
+extern "C" {
+
+int nr_camera_partial_blocks(int32_t num_vertices) { return (num_vertices + nr::CAM_THREADS - 1) / nr::CAM_THREADS; }
+
+int nr_camera_forward(const float *vertices, const float *rotation, const float *eye, float *out, int32_t batch,
+                      int32_t num_vertices, int32_t perspective, float width, void *stream) {
+    if (!vertices || !rotation || !eye || !out || batch < 0 || num_vertices < 0 || batch > 65535) return NR_ERR_INVALID_ARGUMENT;
+    if (batch == 0 || num_vertices == 0) return NR_OK;
+    dim3 grid(nr_camera_partial_blocks(num_vertices), batch);
+    nr::k_camera_forward<<<grid, nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(vertices, rotation, eye, out, num_vertices,
+                                                                            perspective, width);
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+int nr_camera_backward(const float *vertices, const float *rotation, const float *eye, const float *grad_out,
+                       float *grad_vertices, float *partial, int32_t batch, int32_t num_vertices,
+                       int32_t perspective, float width, void *stream) {
+    if (!vertices || !rotation || !eye || !grad_out || !grad_vertices || !partial || batch < 0 || num_vertices < 0 ||
+        batch > 65535)
+        return NR_ERR_INVALID_ARGUMENT;
+    if (batch == 0 || num_vertices == 0) return NR_OK;
+    dim3 grid(nr_camera_partial_blocks(num_vertices), batch);
+    nr::k_camera_backward<<<grid, nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(vertices, rotation, eye, grad_out,
+                                                                             grad_vertices, partial, num_vertices,
+                                                                             perspective, width);
+    return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -6,6 +6,9 @@ New here (the reference has no device logic at all): ``render*`` work on whateve
 inputs live on, and :mod:`.parallel` shards a batch of views over the GPUs of one box."""
 import math
 
+import torch
+
+from . import camera
 from .look import look
 from .look_at import look_at
 from .perspective import perspective
@@ -32,9 +35,16 @@ class Renderer(object):
 
         # not in the reference: bit-reproducible gradients (see RasterizeHyperparam.deterministic)
         self.deterministic = False
+        # not in the reference: one fused kernel for look_at / look + perspective (camera.py)
+        self.fused_camera = True
 
     def transform_vertices(self, vertices, lights=None):
-        """World -> screen space (renderer.py:24-35)."""
+        """World -> screen space (renderer.py:24-35).  CUDA tensors go through the fused camera
+        kernel (camera.py); set ``fused_camera = False`` for the chain of torch ops."""
+        if (self.fused_camera and vertices.is_cuda and not torch.is_tensor(self.viewing_angle)
+                and self.camera_mode in ('look_at', 'look')):
+            return camera.transform_vertices(vertices, self.viewpoints, self.camera_mode, self.camera_direction,
+                                             self.perspective, self.viewing_angle)
         if self.camera_mode == 'look_at':
             vertices = look_at(vertices, self.viewpoints)
         elif self.camera_mode == 'look':

@@ -103,6 +103,31 @@ def test_renderer_end_to_end(nr):
     assert np.abs(gv - gw).max() <= 2e-2 * np.abs(gw).max()
 
 
+@pytest.mark.parametrize("mode,persp", [("look_at", True), ("look_at", False), ("look", True)])
+def test_fused_camera_transform_matches_torch_ops(nr, mode, persp):
+    """camera.transform_vertices (one kernel each way) vs the look_at / look + perspective torch ops:
+    screen vertices to 1e-6, gradients to vertices and to the viewpoints to 1e-4."""
+    g = torch.Generator().manual_seed(3)
+    B, nv = 5, 777
+    v0 = (torch.rand((B, nv, 3), generator=g) - 0.5)
+    e0 = nr.get_points_from_angles(torch.full((B,), 2.7), torch.rand(B, generator=g) * 60 - 20, torch.rand(B, generator=g) * 360)
+    G = torch.randn((B, nv, 3), generator=g).cuda()
+    outs = []
+    for fused in (True, False):
+        v = v0.clone().cuda().requires_grad_(True)
+        e = e0.clone().cuda().requires_grad_(True)
+        r = nr.Renderer()
+        r.camera_mode, r.perspective, r.viewpoints, r.fused_camera = mode, persp, e, fused
+        r.camera_direction = [0.1, -0.2, 1.0]
+        out = r.transform_vertices(v)
+        (out * G).sum().backward()
+        outs.append((out.detach(), v.grad, e.grad))
+    (o1, gv1, ge1), (o0, gv0, ge0) = outs
+    assert torch.allclose(o1, o0, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gv1, gv0, rtol=1e-4, atol=1e-4 * gv0.abs().max().item())
+    assert torch.allclose(ge1, ge0, rtol=1e-3, atol=1e-4 * ge0.abs().max().item())
+
+
 def _fim_cuda(nr, faces_np, R, near=0.1, far=100.0, backside=True):
     f = torch.from_numpy(np.ascontiguousarray(faces_np, dtype=np.float32)).cuda()
     B, nf = f.shape[:2]
