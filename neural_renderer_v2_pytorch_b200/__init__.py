@@ -15,7 +15,8 @@ from .rasterize import (rasterize_silhouettes, rasterize_rgba, rasterize_rgb, ra
                         rasterize_core, rasterize_maps, face_index_map_forward_safe,
                         compute_weight_map_c)
 from .renderer import Renderer
-from .utils import to_gpu, create_textures, get_points_from_angles
+from .save_obj import save_obj
+from .utils import to_gpu, imread, make_gif, create_textures, get_points_from_angles
 from .differentiation import differentiation
 from .graph import capture_step
 from . import parallel

@@ -14,6 +14,25 @@ def to_gpu(data, device=None):
     return torch.as_tensor(data).cuda(device)
 
 
+def imread(filename):
+    """``utils.py:25-27``: image file -> float32 array in [0, 1] (PIL instead of imageio)."""
+    from PIL import Image
+    return np.asarray(Image.open(filename), dtype='float32') / 255.
+
+
+def make_gif(working_directory, filename):
+    """``utils.py:10-15``: assemble ``_tmp_*.png`` frames into a gif (PIL instead of ImageMagick)."""
+    import glob
+    import os
+    from PIL import Image
+    frames = sorted(glob.glob('%s/_tmp_*.png' % working_directory))
+    images = [Image.open(f).convert('RGB') for f in frames]
+    if images:
+        images[0].save(filename, save_all=True, append_images=images[1:], duration=80, loop=0)
+    for f in frames:
+        os.remove(f)
+
+
 def create_textures(num_faces, texture_size=16, flatten=False):
     """Per-face texture atlas (``utils.py:30-52``): face i owns the texture_size^2 block at
     (row, column) = divmod(i, tile_width) and maps its corners to three corners of that block.

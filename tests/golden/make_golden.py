@@ -227,5 +227,31 @@ def main():
          grad_vertices=sq.grad)
 
 
+def make_textured_obj_fixture(nr):
+    """A small synthetic textured mesh (two image materials of different width + one colour
+    material), loaded with the REFERENCE's load_obj(load_textures=True); tests/test_host.py checks this
+    repo's loader against the stored arrays.  The .obj / .mtl / .png files are committed too."""
+    from PIL import Image
+    d = os.path.join(HERE, "textured")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.RandomState(5)
+    Image.fromarray(rng.randint(0, 256, size=(6, 8, 3)).astype("uint8")).save(os.path.join(d, "a.png"))
+    Image.fromarray(rng.randint(0, 256, size=(4, 5, 3)).astype("uint8")).save(os.path.join(d, "b.png"))
+    with open(os.path.join(d, "m.mtl"), "w") as f:
+        f.write("newmtl first\nKd 1 1 1\nmap_Kd a.png\n\nnewmtl second\nmap_Kd b.png\n\nnewmtl flat\nKd 0.25 0.5 0.75\n")
+    with open(os.path.join(d, "m.obj"), "w") as f:
+        f.write("mtllib m.mtl\n")
+        for v in [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0.5, 0.5, 1), (2, 2, 2)]:
+            f.write("v %g %g %g\n" % v)
+        for t in [(0, 0), (1, 0), (1, 1), (0, 1), (0.5, 0.25), (0.2, 0.9)]:
+            f.write("vt %g %g\n" % t)
+        f.write("usemtl first\nf 1/1 2/2 3/3 4/4\nusemtl second\nf 1/5 2/6 5/1\nf 2/2 3/3 5/4\nusemtl flat\nf 3 4 5\nf 4/1 1/2 6/3\n")
+    import imageio
+    imageio.imread = lambda fn: np.asarray(Image.open(fn).convert("RGB"))
+    v, f, vt, ft, tex = nr.load_obj(os.path.join(d, "m.obj"), load_textures=True)
+    save("textured_obj_reference_loader", vertices=v, faces=f, vertices_t=vt, faces_t=ft, textures=tex)
+
+
 if __name__ == "__main__":
     main()
+    make_textured_obj_fixture(import_reference())

@@ -85,6 +85,44 @@ def test_load_obj_matches_reference_loader(tmp_path):
     assert d["vertices"].shape == (1292, 3) and d["faces"].shape == (2464, 3)
 
 
+def test_textured_obj_loader_matches_reference_loader():
+    """load_obj(load_textures=True) vs arrays produced by the REFERENCE's loader on the same files
+    (tests/golden/make_golden.py::make_textured_obj_fixture): two image materials + one colour material."""
+    d = np.load(os.path.join(GOLDEN, "textured_obj_reference_loader.npz"))
+    v, f, vt, ft, tex = nr.load_obj(os.path.join(GOLDEN, "textured", "m.obj"), load_textures=True)
+    for name, a in (("vertices", v), ("faces", f), ("vertices_t", vt), ("faces_t", ft), ("textures", tex)):
+        assert a.dtype == d[name].dtype and np.array_equal(a, d[name]), name
+    with pytest.raises(Exception, match="Failed to load textures"):
+        nr.load_obj(os.path.join(GOLDEN, "..", "..", "tests", "golden", "textured", "no_mtl.obj")
+                    if False else _obj_without_mtl(), load_textures=True)
+
+
+def _obj_without_mtl():
+    import tempfile
+    f = tempfile.NamedTemporaryFile("w", suffix=".obj", delete=False)
+    f.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    f.close()
+    return f.name
+
+
+def test_save_obj_round_trip(tmp_path):
+    """tests_torch/test_save_obj.py in spirit: save -> load returns the same mesh and (8-bit) texture."""
+    v, f, vt, ft, tex = nr.load_obj(os.path.join(GOLDEN, "textured", "m.obj"), load_textures=True, normalization=False)
+    vt_before = vt.copy()
+    p = str(tmp_path / "out.obj")
+    nr.save_obj(p, v, f, vt, ft, tex)
+    assert np.array_equal(vt, vt_before), "save_obj must not modify its arguments"
+    v2, f2, vt2, ft2, tex2 = nr.load_obj(p, load_textures=True, normalization=False)
+    assert np.allclose(v2, v, atol=1e-6) and np.array_equal(f2, f) and np.array_equal(ft2, ft)
+    assert np.allclose(vt2, vt, atol=1e-4) and tex2.shape == tex.shape
+    assert np.abs(tex2 - tex).max() <= 0.5 / 255 + 1e-6
+    nr.save_obj(str(tmp_path / "plain.obj"), v, f)
+    v3, f3 = nr.load_obj(str(tmp_path / "plain.obj"), normalization=False)
+    assert np.allclose(v3, v, atol=1e-6) and np.array_equal(f3, f)
+    img = nr.imread(str(tmp_path / "out.png"))
+    assert img.dtype == np.float32 and img.max() <= 1.0
+
+
 def test_cpu_tensors_are_rejected_not_computed():
     """No CPU fallback: a CPU tensor raises like CHECK_CUDA (rasterize_cuda.cpp:5)."""
     hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False)
