@@ -91,7 +91,9 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
                                                         const float u[3], const float v[3],
                                                         const float g[3], int tap[4], float tw[4],
                                                         int &cell, float gz[3], float gu[3], float gv[3]) {
-    const TexCoord tc = texel_coord(q, z, u, v, eps);
+    // exact divisions like the forward: texel coordinates reach ~1e3, where the fast division's 2 ulp
+    // would move the bilinear weights by more than the 1e-5 gradient tolerance
+    const TexCoord tc = texel_coord<true>(q, z, u, v, eps);
     const float depth = tc.depth, nx = tc.nx, ny = tc.ny, x0 = tc.x0, y0 = tc.y0, xf = tc.xf, yf = tc.yf;
     const float *zz = tc.zz;
     const float ulo = fminf(u[0], fminf(u[1], u[2])), uhi = __fsub_rn(fmaxf(u[0], fmaxf(u[1], u[2])), eps);
@@ -287,7 +289,7 @@ k_backward(const BackwardArgs a) {
         const float xp = pix_center(xi, R), yp = pix_center(yi, R);
         float q[3];
         raw_weights(xp, yp, X[0], Y[0], X[1], Y[1], X[2], Y[2], q[0], q[1], q[2]);
-        normalize_weights(q[0], q[1], q[2]);
+        normalize_weights<true>(q[0], q[1], q[2]);   // exact: 2 ulp on q move texel coordinates of ~1e3 by 1e-4
         float gz[3] = {0.f, 0.f, 0.f};
         int c0 = 0;
         if (rgb) {

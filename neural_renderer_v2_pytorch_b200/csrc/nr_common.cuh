@@ -87,7 +87,15 @@ __device__ __forceinline__ void raw_weights(float xp, float yp, float x0, float 
                    __fmaf_rn(x0, y1, -__fmul_rn(x1, y0)));
 }
 
+// IEEE division where a result must be bit-identical to the reference (everything the FORWARD
+// writes); the backward only needs its gradients to ~1e-6 relative and may use the fast one.
+template <bool EXACT>
+__device__ __forceinline__ float div_f(float a, float b) {
+    return EXACT ? __fdiv_rn(a, b) : __fdividef(a, b);
+}
+
 // compute_weight_map_cuda_kernel, rasterize_cuda_kernel.cu:279-306, from the raw numerators.
+template <bool EXACT = true>
 __device__ __forceinline__ void normalize_weights(float &w0, float &w1, float &w2) {
     if (__fadd_rn(__fadd_rn(w0, w1), w2) < 0.f) {
         w0 = -w0;
@@ -98,9 +106,9 @@ __device__ __forceinline__ void normalize_weights(float &w0, float &w1, float &w
     w1 = fmaxf(w1, 0.f);
     w2 = fmaxf(w2, 0.f);
     const float s = __fadd_rn(__fadd_rn(w0, w1), w2);
-    w0 = fmaxf(fminf(__fdiv_rn(w0, s), 1.f), 0.f);
-    w1 = fmaxf(fminf(__fdiv_rn(w1, s), 1.f), 0.f);
-    w2 = fmaxf(fminf(__fdiv_rn(w2, s), 1.f), 0.f);
+    w0 = fmaxf(fminf(div_f<EXACT>(w0, s), 1.f), 0.f);
+    w1 = fmaxf(fminf(div_f<EXACT>(w1, s), 1.f), 0.f);
+    w2 = fmaxf(fminf(div_f<EXACT>(w2, s), 1.f), 0.f);
 }
 
 // utils.maximum (utils.py:91-101) on scalars.
@@ -119,20 +127,21 @@ struct TexCoord {
     float xf, yf;          // after the clamp to [min corner, max corner - eps]
     float zz[3];           // z + 1e-10
 };
+template <bool EXACT = true>
 __device__ __forceinline__ TexCoord texel_coord(const float q[3], const float z[3], const float u[3],
                                                 const float v[3], float eps) {
     TexCoord t;
     t.zz[0] = __fadd_rn(z[0], 1e-10f);
     t.zz[1] = __fadd_rn(z[1], 1e-10f);
     t.zz[2] = __fadd_rn(z[2], 1e-10f);
-    const float a0 = __fadd_rn(__fdiv_rn(q[0], t.zz[0]), 1e-10f);
-    const float a1 = __fadd_rn(__fdiv_rn(q[1], t.zz[1]), 1e-10f);
-    const float a2 = __fadd_rn(__fdiv_rn(q[2], t.zz[2]), 1e-10f);
-    t.depth = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(a0, a1), a2));
-    t.nx = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(q[0], u[0]), t.zz[0]), __fdiv_rn(__fmul_rn(q[1], u[1]), t.zz[1])),
-                     __fdiv_rn(__fmul_rn(q[2], u[2]), t.zz[2]));
-    t.ny = __fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(q[0], v[0]), t.zz[0]), __fdiv_rn(__fmul_rn(q[1], v[1]), t.zz[1])),
-                     __fdiv_rn(__fmul_rn(q[2], v[2]), t.zz[2]));
+    const float a0 = __fadd_rn(div_f<EXACT>(q[0], t.zz[0]), 1e-10f);
+    const float a1 = __fadd_rn(div_f<EXACT>(q[1], t.zz[1]), 1e-10f);
+    const float a2 = __fadd_rn(div_f<EXACT>(q[2], t.zz[2]), 1e-10f);
+    t.depth = div_f<EXACT>(1.f, __fadd_rn(__fadd_rn(a0, a1), a2));
+    t.nx = __fadd_rn(__fadd_rn(div_f<EXACT>(__fmul_rn(q[0], u[0]), t.zz[0]), div_f<EXACT>(__fmul_rn(q[1], u[1]), t.zz[1])),
+                     div_f<EXACT>(__fmul_rn(q[2], u[2]), t.zz[2]));
+    t.ny = __fadd_rn(__fadd_rn(div_f<EXACT>(__fmul_rn(q[0], v[0]), t.zz[0]), div_f<EXACT>(__fmul_rn(q[1], v[1]), t.zz[1])),
+                     div_f<EXACT>(__fmul_rn(q[2], v[2]), t.zz[2]));
     t.x0 = __fmul_rn(t.nx, t.depth);
     t.y0 = __fmul_rn(t.ny, t.depth);
     t.xf = fminf(fmaxf(t.x0, fminf(u[0], fminf(u[1], u[2]))), __fsub_rn(fmaxf(u[0], fmaxf(u[1], u[2])), eps));
