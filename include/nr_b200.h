@@ -74,6 +74,22 @@ typedef struct nrRasterConfig {
 } nrRasterConfig;
 
 /*
+ * Optional shading (rasterize.py:252-283 with the smooth normal map of :162-190); NULL = unlit.
+ * Light l of view b is data[(l * B + b) * 8 ..]: colour rgb, direction xyz, alpha, unused.
+ * types[l]: 0 ambient (lights.py:22-24), 1 directional (:10-19), 2 specular (:27-39); +4 = backside
+ * (|intensity| instead of relu).  vertex_normals [B, nv, 3] are the normalised per-vertex normals
+ * (sum of the normals of the faces touching the vertex); the backward accumulates into
+ * grad_vertex_normals [B, nv, 3] (caller zero-fills), from where autograd reaches the vertices.
+ */
+typedef struct nrLights {
+    int32_t num_lights;
+    const int32_t *types;        /* [L], device */
+    const float *data;           /* [L, B, 8] */
+    const float *vertex_normals; /* [B, nv, 3] */
+    float *grad_vertex_normals;  /* backward only, may be NULL */
+} nrLights;
+
+/*
  * Written by the forward into the workspace header and, when `stats_host` is given,
  * copied asynchronously to that (pinned) host struct so the caller can look at it once
  * `stats_event` has completed.  overflow != 0 means the (tile, face) pair list did not fit
@@ -151,7 +167,7 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
                          const float *textures, int32_t *face_index_map, float *weight_map,
                          float *depth_map, float *images, float *images_internal, int32_t *tile_list,
                          void *workspace, size_t workspace_bytes, int64_t pair_capacity,
-                         nrBinStats *stats_host, void *stats_event, void *stream);
+                         nrBinStats *stats_host, void *stats_event, const nrLights *lights, void *stream);
 
 /*
  * Fused backward: AA / flip / permute backward, the Differentiation stencil
@@ -177,7 +193,8 @@ NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertice
                           const float *textures, const int32_t *face_index_map,
                           const float *images_internal, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
-                          float *grad_vertices_textures, void *deterministic_scratch, void *stream);
+                          float *grad_vertices_textures, void *deterministic_scratch, const nrLights *lights,
+                          void *stream);
 
 /*
  * Differentiation.backward (differentiation.py:13-36) on channels-last tensors, as the

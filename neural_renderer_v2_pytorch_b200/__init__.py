@@ -6,6 +6,7 @@ everything on that path; the kernels are hand-written sm_100a CUDA behind a C AB
 (``include/nr_b200.h``, ``csrc/``).  No CPU or PyTorch fallback exists: importing works anywhere,
 calling an operator without the built library or without a CUDA tensor raises.
 """
+from .lights import Light, DirectionalLight, AmbientLight, SpecularLight
 from .load_obj import load_obj
 from .look import look
 from .look_at import look_at

@@ -47,6 +47,12 @@ class RasterConfig(ctypes.Structure):
     ]
 
 
+class Lights(ctypes.Structure):
+    """``nrLights``."""
+    _fields_ = [("num_lights", ctypes.c_int32), ("types", ctypes.c_void_p), ("data", ctypes.c_void_p),
+                ("vertex_normals", ctypes.c_void_p), ("grad_vertex_normals", ctypes.c_void_p)]
+
+
 class BinStats(ctypes.Structure):
     """``nrBinStats``."""
     _fields_ = [("total_pairs", ctypes.c_int32), ("max_tile_faces", ctypes.c_int32),
@@ -102,9 +108,9 @@ def lib():
     L.nr_workspace_bytes.argtypes = [ctypes.POINTER(RasterConfig), i64]
     L.nr_rasterize_forward.restype = ctypes.c_int
     L.nr_rasterize_forward.argtypes = [ctypes.POINTER(RasterConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, vp]
+                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, ctypes.POINTER(Lights), vp]
     L.nr_rasterize_backward.restype = ctypes.c_int
-    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 14
+    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 13 + [ctypes.POINTER(Lights), vp]
     L.nr_deterministic_scratch_bytes.restype = ctypes.c_size_t
     L.nr_deterministic_scratch_bytes.argtypes = [ctypes.POINTER(RasterConfig)]
     L.nr_differentiation_backward.restype = ctypes.c_int

@@ -175,7 +175,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
                          const float *textures, int32_t *face_index_map, float *weight_map,
                          float *depth_map, float *images, float *images_internal, int32_t *tile_list,
                          void *workspace, size_t workspace_bytes, int64_t pair_capacity,
-                         nrBinStats *stats_host, void *stats_event, void *stream_) {
+                         nrBinStats *stats_host, void *stats_event, const nrLights *lights, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
@@ -243,6 +243,14 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.dmap = depth_map;
     ra.images = images;
     ra.internal = images_internal;
+    ra.faces = faces;
+    ra.nv = cfg->num_vertices;
+    ra.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr};
+    if (lights && lights->num_lights > 0 && rgb) {
+        if (!lights->types || !lights->data || !lights->vertex_normals)
+            return fail(NR_ERR_INVALID_ARGUMENT, "lights: types, data and vertex_normals are required");
+        ra.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals, nullptr};
+    }
 
     // fork: background fill on the side stream, binning on the caller's stream
     cudaError_t e;
@@ -277,7 +285,8 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
                           const float *textures, const int32_t *face_index_map,
                           const float *images_internal, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
-                          float *grad_vertices_textures, void *deterministic_scratch, void *stream_) {
+                          float *grad_vertices_textures, void *deterministic_scratch, const nrLights *lights,
+                          void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
     if (!vertices || !face_index_map || !images_internal || !grad_images || !grad_vertices)
@@ -299,6 +308,13 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
     a.grad_verts = grad_vertices;
     a.grad_tex = grad_textures;
     a.grad_vt = grad_vertices_textures;
+    a.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr};
+    if (lights && lights->num_lights > 0 && rgb) {
+        if (!lights->types || !lights->data || !lights->vertex_normals)
+            return fail(NR_ERR_INVALID_ARGUMENT, "lights: types, data and vertex_normals are required");
+        a.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals,
+                                 lights->grad_vertex_normals};
+    }
     a.det_verts = a.det_tex = a.det_vt = nullptr;
     a.det_scale = 4294967296.f;     // 2^32: resolution 2.3e-10, |sum| < 2.1e9
     if (cfg->flags & NR_DETERMINISTIC) {
@@ -386,7 +402,7 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
         }
         s.pair_capacity = cap;
         int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
-                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, stream);
+                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, nullptr, stream);
         if (rc != NR_OK) return rc;
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");

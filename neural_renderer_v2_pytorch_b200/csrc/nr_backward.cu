@@ -89,7 +89,8 @@ template <bool NEED_UV>
 __device__ __forceinline__ void sample_texture_backward(const float *__restrict__ tex_b, int H, int W,
                                                         float eps, const float q[3], const float z[3],
                                                         const float u[3], const float v[3],
-                                                        const float g[3], int tap[4], float tw[4],
+                                                        const float g_lit[3], const float cw[3], float g[3],
+                                                        float rgb_tex[3], int tap[4], float tw[4],
                                                         int &cell, float gz[3], float gu[3], float gv[3]) {
     // exact divisions like the forward: texel coordinates reach ~1e3, where the fast division's 2 ulp
     // would move the bilinear weights by more than the 1e-5 gradient tolerance
@@ -105,14 +106,21 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
     const int T = H * W;
     tap[0] = yfi * W + xfi; tap[1] = yfi * W + xci; tap[2] = yci * W + xfi; tap[3] = yci * W + xci;
     cell = (yfi << 16) ^ (xfi & 0xffff);   // identifies the bilinear cell: equal cell => equal four taps
+    // g = upstream gradient of the UNLIT sample (lit = unlit * cw, rasterize.py:283); rgb_tex = unlit sample
     float d[4];
+    g[0] = g_lit[0] * cw[0]; g[1] = g_lit[1] * cw[1]; g[2] = g_lit[2] * cw[2];
+    rgb_tex[0] = rgb_tex[1] = rgb_tex[2] = 0.f;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         if ((unsigned)tap[t] >= (unsigned)T) tap[t] = -1;
         d[t] = 0.f;
         if (tap[t] >= 0) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) d[t] += g[c] * __ldg(tex_b + (size_t)c * T + tap[t]);
+            for (int c = 0; c < 3; ++c) {
+                const float tv = __ldg(tex_b + (size_t)c * T + tap[t]);
+                d[t] += g[c] * tv;
+                rgb_tex[c] += tw[t] * tv;
+            }
         }
     }
     const float gxf = ay * (d[1] - d[0]) + by * (d[3] - d[2]);
@@ -293,8 +301,8 @@ k_backward(const BackwardArgs a) {
         float gz[3] = {0.f, 0.f, 0.f};
         int c0 = 0;
         if (rgb) {
-            const float g[3] = {gcen[0], gcen[1], gcen[2]};
-            if (g[0] != 0.f || g[1] != 0.f || g[2] != 0.f) {
+            const float g_lit[3] = {gcen[0], gcen[1], gcen[2]};
+            if (g_lit[0] != 0.f || g_lit[1] != 0.f || g_lit[2] != 0.f) {
                 const int32_t *fti = a.ft + 3 * (size_t)f;
                 const float *vtb = a.vt + (size_t)b * a.nvt * 2;
                 int tvid[3];
@@ -306,9 +314,32 @@ k_backward(const BackwardArgs a) {
                     u[k] = uv.x;
                     v[k] = uv.y;
                 }
-                float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f}, tw[4];
-                sample_texture_backward<NEED_UV>(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g,
-                                        tap, tw, cell, gz, gu, gv);
+                float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f}, tw[4], g[3], rgb_tex[3];
+                float cw[3] = {1.f, 1.f, 1.f}, nrm[3] = {0.f, 0.f, 0.f};
+                const bool lit = a.lights.num > 0;
+                if (lit) {
+                    const float *vnb = a.lights.vnormals + (size_t)b * a.nv * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            nrm[c] = __fadd_rn(nrm[c], __fmul_rn(q[k], __ldg(vnb + 3 * (size_t)vid[k] + c)));
+                    light_weights(a.lights, b, a.B, nrm, cw, nullptr, nullptr);
+                }
+                sample_texture_backward<NEED_UV>(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g_lit,
+                                        cw, g, rgb_tex, tap, tw, cell, gz, gu, gv);
+                if (lit && a.lights.grad_vnormals) {
+                    // d loss / d colour weight = upstream * unlit sample; then through the lights to the normal
+                    const float gcw[3] = {g_lit[0] * rgb_tex[0], g_lit[1] * rgb_tex[1], g_lit[2] * rgb_tex[2]};
+                    float cw2[3], gn[3];
+                    light_weights(a.lights, b, a.B, nrm, cw2, gcw, gn);
+                    float *gvn = a.lights.grad_vnormals + (size_t)b * a.nv * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (gn[c] != 0.f) atomicAdd(gvn + 3 * (size_t)vid[k] + c, q[k] * gn[c]);
+                }
                 has_tex = true;
 #pragma unroll
                 for (int t = 0; t < 4; ++t)

@@ -149,6 +149,53 @@ __device__ __forceinline__ TexCoord texel_coord(const float q[3], const float z[
     return t;
 }
 
+// Lights as the kernels see them (include/nr_b200.h: nrLights).
+struct LightArgs {
+    int num;
+    const int32_t *types;
+    const float *data;       // [L, B, 8]
+    const float *vnormals;   // [B, nv, 3]
+    float *grad_vnormals;    // backward
+};
+
+// Colour weight of one pixel from its interpolated normal n (rasterize.py:256-282), and when
+// gn != nullptr the gradient of  sum_c gcw[c] * cw[c]  with respect to n.
+__device__ __forceinline__ void light_weights(const LightArgs &L, int b, int B, const float n[3], float cw[3],
+                                              const float *gcw, float *gn) {
+    cw[0] = cw[1] = cw[2] = 0.f;
+    if (gn) gn[0] = gn[1] = gn[2] = 0.f;
+    for (int l = 0; l < L.num; ++l) {
+        const int type = __ldg(L.types + l);
+        const float *d = L.data + ((size_t)l * B + b) * 8;
+        const float cr = __ldg(d), cg = __ldg(d + 1), cb = __ldg(d + 2);
+        const int kind = type & 3;
+        if (kind == 0) {
+            cw[0] = __fadd_rn(cw[0], cr); cw[1] = __fadd_rn(cw[1], cg); cw[2] = __fadd_rn(cw[2], cb);
+            continue;
+        }
+        float dir[3] = {0.f, 0.f, 1.f};                     // specular: direction_eye (rasterize.py:271)
+        if (kind == 1) { dir[0] = __ldg(d + 3); dir[1] = __ldg(d + 4); dir[2] = __ldg(d + 5); }
+        const float raw = __fadd_rn(__fadd_rn(__fmul_rn(-dir[0], n[0]), __fmul_rn(-dir[1], n[1])), __fmul_rn(-dir[2], n[2]));
+        const bool backside = (type & 4) != 0;
+        const float a = backside ? fabsf(raw) : fmaxf(raw, 0.f);
+        const float gate = backside ? (raw > 0.f ? 1.f : (raw < 0.f ? -1.f : 0.f)) : (raw > 0.f ? 1.f : 0.f);
+        float inten = a, dinten = gate;                     // d inten / d raw
+        if (kind == 2) {
+            const float alpha = __ldg(d + 6);
+            inten = powf(a, alpha);
+            dinten = gate * alpha * powf(a, alpha - 1.f);
+            if (gate == 0.f) dinten = 0.f;
+        }
+        cw[0] = __fadd_rn(cw[0], __fmul_rn(inten, cr));
+        cw[1] = __fadd_rn(cw[1], __fmul_rn(inten, cg));
+        cw[2] = __fadd_rn(cw[2], __fmul_rn(inten, cb));
+        if (gn) {
+            const float gi = (gcw[0] * cr + gcw[1] * cg + gcw[2] * cb) * dinten;
+            gn[0] -= gi * dir[0]; gn[1] -= gi * dir[1]; gn[2] -= gi * dir[2];
+        }
+    }
+}
+
 // Thread -> pixel mapping inside a tile: warp w owns the 8x4 block at
 // ((w & 1) * 8, (w >> 1) * 4); lane l is pixel (l & 7, l >> 3) of the block.
 __device__ __forceinline__ void tile_pixel(int tid, int &px, int &py) {

@@ -53,6 +53,9 @@ struct RasterArgs {
     float *dmap;            // [B, R, R] or null
     float *images;          // [B, C, S, S] or null (compat call renders no image)
     float *internal;        // [B, C, R, R] (AA) or null
+    const int32_t *faces;   // [nf, 3] vertex ids (null: 3f..3f+2), only read when lights are on
+    int nv;
+    LightArgs lights;
 };
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream);
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);
@@ -73,6 +76,7 @@ struct BackwardArgs {
     // laid out back to back) and the power-of-two scale; null = float atomics
     long long *det_verts, *det_tex, *det_vt;
     float det_scale;
+    LightArgs lights;
     int B, nv, nf, R, S, ntx, C, flags, nvt, H, W;
     float eps;
 };

@@ -292,6 +292,19 @@ k_raster(const RasterArgs a) {
                     }
                     const float z[3] = {bz0, bz1, bz2};
                     sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
+                    if (a.lights.num > 0) {
+                        // smooth normal map (rasterize.py:186-187) and light accumulation (:252-283)
+                        float n[3] = {0.f, 0.f, 0.f}, cw[3];
+                        const float *vnb = a.lights.vnormals + (size_t)b * a.nv * 3;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int vid = a.faces ? __ldg(a.faces + 3 * (size_t)best + k) : 3 * best + k;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) n[c] = __fadd_rn(n[c], __fmul_rn(q[k], __ldg(vnb + 3 * (size_t)vid + c)));
+                        }
+                        light_weights(a.lights, b, a.B, n, cw, nullptr, nullptr);
+                        rgb[0] = __fmul_rn(rgb[0], cw[0]); rgb[1] = __fmul_rn(rgb[1], cw[1]); rgb[2] = __fmul_rn(rgb[2], cw[2]);
+                    }
                 }
                 put(0, rgb[0]);
                 put(1, rgb[1]);

@@ -7,15 +7,15 @@ torch ops with per-view host synchronisation.
 Differences from the reference that are deliberate (DESIGN.md "API notes"):
   * ``hyperparams.image_size`` is NOT doubled in place when anti-aliasing is on
     (the reference mutates the caller's object, rasterize.py:227-228);
-  * ``lights`` / ``backgrounds`` / ``background_color`` are outside the accelerated path
-    (lights are a "next" row; backgrounds are broken in the reference,
-    rasterize.py:156-159) and raise ``NotImplementedError``.
+  * ``backgrounds`` / ``background_color`` raise ``NotImplementedError`` (broken in the reference,
+    rasterize.py:156-159: ``.astype`` / ``[::-1]`` on tensors).
 """
 import ctypes
 
 import torch
 
 from . import _lib
+from . import lights as light_lib
 from .rasterize_param import RasterizeParam, RasterizeHyperparam
 
 DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
@@ -115,7 +115,17 @@ def _flags_of(hp):
             (_lib.NR_DETERMINISTIC if (DETERMINISTIC or getattr(hp, "deterministic", False)) else 0))
 
 
-def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
+def _lights_struct(lights, grad_vn=None):
+    """lights = (types, data, vertex_normals) or None -> ctypes nrLights pointer or None."""
+    if lights is None:
+        return None
+    types, data, vn = lights
+    return ctypes.byref(_lib.Lights(num_lights=types.shape[0], types=types.data_ptr(), data=data.data_ptr(),
+                                    vertex_normals=vn.data_ptr(),
+                                    grad_vertex_normals=grad_vn.data_ptr() if grad_vn is not None else None))
+
+
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None):
     """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
     Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
@@ -159,7 +169,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps):
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
             ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
             ctypes.c_void_p(sc.stats.data_ptr()) if track else None, sc.event if track else None,
-            ctypes.c_void_p(stream))
+            _lights_struct(lights), ctypes.c_void_p(stream))
         _lib.check(rc, "nr_rasterize_forward")
         if track:
             sc.pending = True
@@ -189,16 +199,23 @@ class _Rasterize(torch.autograd.Function):
     every autograd edge the reference has on this path)."""
 
     @staticmethod
-    def forward(ctx, vertices, vertices_textures, textures, faces, faces_textures, cfg):
+    def forward(ctx, vertices, vertices_textures, textures, vertex_normals, faces, faces_textures, cfg, light_pack):
         v = _f32c(vertices)
         vt = _f32c(vertices_textures) if vertices_textures is not None else None
         tex = _f32c(textures) if textures is not None else None
-        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False)
+        lights = None
+        if light_pack is not None:
+            lights = (light_pack[0], light_pack[1], _f32c(vertex_normals))
+        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights)
         ctx.cfg = cfg
         ctx.has_tex = tex is not None
+        ctx.has_lights = lights is not None
+        ctx.in_dtypes = tuple(t.dtype if t is not None else None for t in (vertices, vertices_textures, textures, vertex_normals))
         saved = [v, faces, fim, internal if internal is not None else images, tile_list]
         if ctx.has_tex:
             saved += [vt, faces_textures, tex]
+        if ctx.has_lights:
+            saved += list(lights)
         ctx.save_for_backward(*saved)
         return images
 
@@ -206,10 +223,14 @@ class _Rasterize(torch.autograd.Function):
     def backward(ctx, grad_images):
         cfg = ctx.cfg
         L = _lib.lib()
+        saved = list(ctx.saved_tensors)
+        lights = tuple(saved[-3:]) if ctx.has_lights else None
+        if ctx.has_lights:
+            saved = saved[:-3]
         if ctx.has_tex:
-            v, faces, fim, internal, tile_list, vt, ft, tex = ctx.saved_tensors
+            v, faces, fim, internal, tile_list, vt, ft, tex = saved
         else:
-            v, faces, fim, internal, tile_list = ctx.saved_tensors
+            v, faces, fim, internal, tile_list = saved
             vt = ft = tex = None
         g = _f32c(grad_images)
         need_v, need_vt, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -219,14 +240,18 @@ class _Rasterize(torch.autograd.Function):
             gv = torch.zeros_like(v)
             gvt = torch.zeros_like(vt) if (need_vt and vt is not None) else None
             gtex = torch.zeros_like(tex) if (need_tex and tex is not None) else None
+            gvn = torch.zeros_like(lights[2]) if (lights is not None and ctx.needs_input_grad[3]) else None
             scratch = None
             if cfg.flags & _lib.NR_DETERMINISTIC:
                 scratch = torch.zeros(L.nr_deterministic_scratch_bytes(ctypes.byref(cfg)) // 8, dtype=torch.int64, device=dev)
             rc = L.nr_rasterize_backward(ctypes.byref(cfg), _ptr(v), _ptr(faces), _ptr(vt), _ptr(ft),
                                          _ptr(tex), _ptr(fim), _ptr(internal), _ptr(tile_list), _ptr(g), _ptr(gv),
-                                         _ptr(gtex), _ptr(gvt), _ptr(scratch), ctypes.c_void_p(stream))
+                                         _ptr(gtex), _ptr(gvt), _ptr(scratch), _lights_struct(lights, gvn),
+                                         ctypes.c_void_p(stream))
             _lib.check(rc, "nr_rasterize_backward")
-        return (gv if need_v else None), gvt, gtex, None, None, None
+        cast = lambda g_, dt: g_.to(dt) if (g_ is not None and dt is not None and g_.dtype != dt) else g_
+        dv, dvt, dtex, dvn = ctx.in_dtypes
+        return (cast(gv, dv) if need_v else None), cast(gvt, dvt), cast(gtex, dtex), cast(gvn, dvn), None, None, None, None
 
 
 def _prepare(vertices, faces, params, hyperparams):
@@ -236,8 +261,6 @@ def _prepare(vertices, faces, params, hyperparams):
     assert faces.ndim == 2
     assert faces.shape[1] == 3
     _require_cuda(vertices, "vertices")
-    if params.lights is not None:
-        raise NotImplementedError("lights are outside the accelerated path (SURVEY.md section 8f)")
     if params.backgrounds is not None or params.background_color is not None:
         raise NotImplementedError("backgrounds are outside the accelerated path (and broken in the "
                                   "reference, rasterize.py:156-159)")
@@ -266,23 +289,29 @@ def _prepare(vertices, faces, params, hyperparams):
         _validate_indices(torch.as_tensor(params.faces_textures), nvt, "faces_textures")
     cfg = _make_config(B, nv, nf, int(hyperparams.image_size), _flags_of(hyperparams), hyperparams,
                        nvt, H, W)
-    return cfg, faces_d, vt, ft, tex
+    light_pack = vn = None
+    if hyperparams.draw_rgb and params.lights:
+        # shading: per-vertex normals by differentiable torch ops (O(nv + nf)), the per-pixel part in the kernels
+        light_pack = light_lib.pack_lights(params.lights, B, dev)
+        vn = light_lib.vertex_normals(vertices, faces_d)
+    return cfg, faces_d, vt, ft, tex, vn, light_pack
 
 
 def rasterize_core(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
     """``rasterize.py:194-329``. vertices [B,nv,3] screen space, faces [nf,3] -> images [B,C,S,S]."""
-    cfg, faces_d, vt, ft, tex = _prepare(vertices, faces, params, hyperparams)
-    return _Rasterize.apply(vertices, vt, tex, faces_d, ft, cfg)
+    cfg, faces_d, vt, ft, tex, vn, light_pack = _prepare(vertices, faces, params, hyperparams)
+    return _Rasterize.apply(vertices, vt, tex, vn, faces_d, ft, cfg, light_pack)
 
 
 def rasterize_maps(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
     """Non-differentiable view of the internal maps the reference builds inside rasterize_core
     (``face_index_map`` :235, ``weight_map`` :236, depth :292) plus the images.  Test / debug aid."""
-    cfg, faces_d, vt, ft, tex = _prepare(vertices, faces, params, hyperparams)
+    cfg, faces_d, vt, ft, tex, vn, light_pack = _prepare(vertices, faces, params, hyperparams)
     with torch.no_grad():
         images, internal, fim, wmap, dmap, _ = _forward_call(
             cfg, _f32c(vertices), faces_d, _f32c(vt) if vt is not None else None, ft,
-            _f32c(tex) if tex is not None else None, True)
+            _f32c(tex) if tex is not None else None, True,
+            (light_pack[0], light_pack[1], _f32c(vn)) if light_pack is not None else None)
     return dict(images=images, internal_images=internal if internal is not None else images,
                 face_index_map=fim, weight_map=wmap, depth_map=dmap)
 

@@ -143,9 +143,46 @@ def compute_coordinate_map(faces, fim, wmap):
     return torch.sum(faces_map * wmap[..., None], -2)
 
 
+def compute_normal_map(vertices, faces_idx, faces, fim, wmap):
+    """``rasterize.py:162-190`` (smooth=True): face normals summed onto their vertices (each vertex
+    once per face), normalised, interpolated with the weight map."""
+    v01 = faces[:, :, 1, :] - faces[:, :, 0, :]
+    v12 = faces[:, :, 2, :] - faces[:, :, 1, :]
+    n = torch.linalg.cross(v01, v12, dim=-1)                         # [B,nf,3]
+    nf, nv = faces_idx.shape[0], vertices.shape[1]
+    m = torch.zeros((nf, nv), dtype=torch.float32)
+    for k in range(3):
+        m[torch.arange(nf), faces_idx[:, k]] = 1
+    vn = torch.matmul(n.permute(0, 2, 1), m).permute(0, 2, 1)        # [B,nv,3]
+    vn = F.normalize(vn, dim=2)
+    normal_map = to_map(vn[:, faces_idx], fim)                       # [B,R,R,3,3]
+    return torch.sum(wmap[..., None] * normal_map, dim=-2)
+
+
+def light_color_weights(normal_map, lights):
+    """``rasterize.py:252-283``. lights: list of dicts {type: ambient|directional|specular, color [B,3],
+    direction [B,3], alpha [B], backside}."""
+    cw = torch.zeros_like(normal_map)
+    for L in lights:
+        color = L["color"][:, None, None, :]
+        if L["type"] == "ambient":
+            cw = cw + color.expand(cw.shape)
+            continue
+        if L["type"] == "directional":
+            intensity = torch.sum(-L["direction"][:, None, None, :] * normal_map, -1)
+        else:
+            eye = torch.tensor([0., 0., 1.])
+            intensity = torch.sum(-eye[None, None, None, :] * normal_map, -1)
+        intensity = torch.abs(intensity) if L.get("backside") else torch.relu(intensity)
+        if L["type"] == "specular":
+            intensity = intensity ** L["alpha"][:, None, None]
+        cw = cw + intensity[..., None] * color
+    return cw
+
+
 def rasterize(vertices, faces, image_size, anti_aliasing, near=0.1, far=100.0, eps=1e-5,
               draw_backside=True, draw_rgb=False, draw_silhouettes=True, draw_depth=False,
-              vertices_textures=None, faces_textures=None, textures=None, return_maps=False):
+              vertices_textures=None, faces_textures=None, textures=None, lights=None, return_maps=False):
     """``rasterize.py:194-329`` (``rasterize_core``) without lights / backgrounds.
 
     vertices [B,nv,3] screen space (may require grad), faces [nf,3] int.
@@ -163,7 +200,10 @@ def rasterize(vertices, faces, image_size, anti_aliasing, near=0.1, far=100.0, e
     chans = []
     if draw_rgb:
         ft = vertices_textures[:, torch.as_tensor(np.asarray(faces_textures)).long()]
-        chans.append(sample_textures(fv, ft, textures, fim, wmap, eps))
+        rgb = sample_textures(fv, ft, textures, fim, wmap, eps)
+        if lights is not None:
+            rgb = rgb * light_color_weights(compute_normal_map(vertices, fidx, fv, fim, wmap), lights)
+        chans.append(rgb)
     if draw_silhouettes:
         chans.append((0 <= fim).to(torch.float32)[..., None])
     if draw_depth:

@@ -227,6 +227,44 @@ def main():
          grad_vertices=sq.grad)
 
 
+def make_lights_fixture(nr):
+    """rasterize_rgb with Directional + Ambient + Specular lights (the setup of
+    tests_torch/test_rasterize.py:114-203, per-view colours / directions from a seed), forward and
+    gradients to vertices and textures: the reference's compute_normal_map (rasterize.py:162-190) and
+    light accumulation (rasterize.py:252-283) executing on CPU."""
+    from neural_renderer_torch.rasterize_param import RasterizeParam, RasterizeHyperparam
+    d = np.load(os.path.join(HERE, "teapot.npz"))
+    v_np, f_np = d["vertices"], d["faces"]
+    nf = f_np.shape[0]
+    for name, B, S, aa, backside, lb in (("lit_rgb_48", 2, 48, False, True, False), ("lit_rgb_aa_24", 2, 24, True, False, True)):
+        g = torch.Generator().manual_seed(40 + S)
+        vw = torch.as_tensor(v_np)[None].repeat(B, 1, 1)
+        vs = screen_space(nr, vw, cameras(nr, B, 50 + S)).detach().clone().requires_grad_(True)
+        vt_np, ft_np, tex_np = nr.create_textures(nf, texture_size=2)
+        tex = torch.rand((B,) + tex_np.shape, generator=g).requires_grad_(True)
+        vt = torch.as_tensor(vt_np)[None].repeat(B, 1, 1)
+        dir_color, dir_dir = torch.rand((B, 3), generator=g), F_normalize(torch.randn((B, 3), generator=g))
+        amb_color, spec_color = torch.rand((B, 3), generator=g) * 0.4, torch.rand((B, 3), generator=g) * 0.5
+        spec_alpha = torch.rand(B, generator=g) * 3 + 1
+        lights = [nr.DirectionalLight(dir_color.clone(), dir_dir.clone(), backside=lb), nr.AmbientLight(amb_color.clone()),
+                  nr.SpecularLight(spec_color.clone(), spec_alpha.clone(), backside=lb)]
+        hp = RasterizeHyperparam(image_size=S, anti_aliasing=aa, draw_backside=backside)
+        params = RasterizeParam(vertices_textures=vt, faces_textures=torch.as_tensor(ft_np), textures=tex, lights=lights)
+        images = nr.rasterize_rgb(vs, torch.as_tensor(f_np), params, hp)
+        G = torch.randn(images.shape, generator=torch.Generator().manual_seed(1))
+        (images * G).sum().backward()
+        save(name, vertices=vs.detach(), faces=f_np.astype(np.int32), image_size=S, anti_aliasing=int(aa),
+             draw_backside=int(backside), near=0.1, far=100.0, mode="rgb", images=images, grad_images=G,
+             grad_vertices=vs.grad, vertices_textures=vt, faces_textures=ft_np.astype(np.int32), textures=tex.detach(),
+             grad_textures=tex.grad, grad_vertices_textures=np.zeros_like(vt.numpy()),
+             dir_color=dir_color, dir_direction=dir_dir, amb_color=amb_color, spec_color=spec_color,
+             spec_alpha=spec_alpha, light_backside=int(lb))
+
+
+def F_normalize(t):
+    return t / t.norm(dim=-1, keepdim=True)
+
+
 def make_textured_obj_fixture(nr):
     """A small synthetic textured mesh (two image materials of different width + one colour
     material), loaded with the REFERENCE's load_obj(load_textures=True); tests/test_host.py checks this
@@ -255,3 +293,4 @@ def make_textured_obj_fixture(nr):
 if __name__ == "__main__":
     main()
     make_textured_obj_fixture(import_reference())
+    make_lights_fixture(import_reference())

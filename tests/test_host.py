@@ -152,10 +152,37 @@ def test_out_of_scope_features_say_so():
     hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False, draw_rgb=False, draw_depth=False)
     v = torch.zeros(1, 3, 3)
     f = torch.tensor([[0, 1, 2]])
-    for p in (nr.RasterizeParam(lights=[object()]), nr.RasterizeParam(background_color=[0, 0, 0]),
+    for p in (nr.RasterizeParam(background_color=[0, 0, 0]),
               nr.RasterizeParam(backgrounds=torch.zeros(1, 3, 16, 16))):
         with pytest.raises((NotImplementedError, RuntimeError)):
             _prepare(v, f, p, hp)
+
+
+def test_vertex_normals_match_the_dense_incidence_formulation():
+    """lights.vertex_normals (index_add) vs the reference's [nf,nv] incidence matmul (rasterize.py:167-182),
+    including a face that lists the same vertex twice (counted once)."""
+    from neural_renderer_v2_pytorch_b200.lights import vertex_normals
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(2, 7, 3, generator=g)
+    f = torch.tensor([[0, 1, 2], [2, 3, 4], [4, 5, 6], [0, 2, 4], [1, 1, 3]], dtype=torch.int32)
+    fv = v[:, f.long()]
+    n = torch.linalg.cross(fv[:, :, 1] - fv[:, :, 0], fv[:, :, 2] - fv[:, :, 1], dim=-1)
+    m = torch.zeros(5, 7)
+    for k in range(3):
+        m[torch.arange(5), f[:, k].long()] = 1
+    want = torch.nn.functional.normalize(torch.matmul(n.permute(0, 2, 1), m).permute(0, 2, 1), dim=2)
+    assert torch.allclose(vertex_normals(v, f), want, atol=1e-6)
+
+
+def test_light_classes_and_packing():
+    B = 3
+    lights = [nr.DirectionalLight(torch.rand(B, 3), torch.rand(B, 3), backside=True), nr.AmbientLight(torch.rand(B, 3)),
+              nr.SpecularLight(torch.rand(B, 3))]
+    assert torch.equal(lights[2].alpha, torch.ones(B))
+    from neural_renderer_v2_pytorch_b200.lights import pack_lights
+    types, data = pack_lights(lights, B, "cpu")
+    assert types.tolist() == [1 | 4, 0, 2] and data.shape == (3, B, 8)
+    assert torch.equal(data[0, :, 3:6], lights[0].direction) and torch.equal(data[2, :, 6], torch.ones(B))
 
 
 def test_bench_bytes_formula():

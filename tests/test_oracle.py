@@ -88,6 +88,29 @@ def test_pipeline_oracle_matches_reference_python(name):
             1e-6 * max(np.abs(d["grad_vertices_textures"]).max(), 1e-30)
 
 
+def lights_of(d):
+    lb = bool(d["light_backside"])
+    t = lambda k: torch.from_numpy(d[k])
+    return [dict(type="directional", color=t("dir_color"), direction=t("dir_direction"), backside=lb),
+            dict(type="ambient", color=t("amb_color")),
+            dict(type="specular", color=t("spec_color"), alpha=t("spec_alpha"), backside=lb)]
+
+
+@pytest.mark.parametrize("name", ["lit_rgb_48", "lit_rgb_aa_24"])
+def test_lighting_oracle_matches_reference_python(name):
+    """compute_normal_map + light accumulation (rasterize.py:162-190, 252-283) as executed by the reference."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    v = torch.from_numpy(d["vertices"]).requires_grad_(True)
+    tex = torch.from_numpy(d["textures"]).requires_grad_(True)
+    img = ref.rasterize(v, d["faces"], int(d["image_size"]), bool(d["anti_aliasing"]), draw_backside=bool(d["draw_backside"]),
+                        draw_rgb=True, draw_silhouettes=False, vertices_textures=torch.from_numpy(d["vertices_textures"]),
+                        faces_textures=d["faces_textures"], textures=tex, lights=lights_of(d))
+    (img * torch.from_numpy(d["grad_images"])).sum().backward()
+    assert np.array_equal(img.detach().numpy(), d["images"])
+    assert np.abs(v.grad.numpy() - d["grad_vertices"]).max() <= 1e-6 * np.abs(d["grad_vertices"]).max()
+    assert np.abs(tex.grad.numpy() - d["grad_textures"]).max() <= 1e-6 * np.abs(d["grad_textures"]).max()
+
+
 @pytest.mark.parametrize("name", ["c1", "c3", "c4", "binary"])
 def test_differentiation_oracle(name):
     d = np.load(os.path.join(GOLDEN, "diff_known_answer_%s.npz" % name))
