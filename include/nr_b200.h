@@ -152,9 +152,10 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   images_internal     [B, C, R, R] out, required with NR_ANTI_ALIASING (the backward
  *                                    stencil runs at internal resolution), else may be NULL
  *                                    (then `images` itself is the internal image)
- *   tile_list           [4 + 4 * B * ceil(R/16)^2] i32 out, optional, 16-byte aligned: element 0 =
- *                       number of non-empty 16x16 tiles, then 4 ints per tile (view, tile_x |
- *                       tile_y << 16, list offset, list length).  Pass it to
+ *   tile_list           [8 + 16 * B * ceil(R/16)^2] i32 out, optional, 16-byte aligned: the non-empty
+ *                       16x16 tiles in four length classes (longest face lists first); elements 0..3
+ *                       = entries per class, then 4 ints per tile (view, tile_x | tile_y << 16, list
+ *                       offset, list length), class k starting at entry k * B * tiles.  Pass it to
  *                       nr_rasterize_backward so the backward visits only those tiles.
  *   workspace           nr_workspace_bytes(cfg, pair_capacity) bytes, 256-byte aligned
  *   stats_host          optional pinned host nrBinStats

@@ -51,7 +51,7 @@ Carve carve(void *base, int B, int nf, int R, long long pair_capacity) {
     c.pairs = (int32_t *)(p + off);
     off = align256(off + (size_t)(pair_capacity > 0 ? pair_capacity : 1) * sizeof(int32_t));
     c.tile_list = (int32_t *)(p + off);
-    off = align256(off + (nr::TILE_LIST_HDR + nr::TILE_ENTRY_INTS * nt) * sizeof(int32_t));
+    off = align256(off + (nr::TILE_LIST_HDR + nr::TILE_ENTRY_INTS * nr::TILE_CLASSES * nt) * sizeof(int32_t));
     c.bytes = off;
     return c;
 }

@@ -200,11 +200,13 @@ k_backward(const BackwardArgs a) {
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
     const int R = a.R, S = a.S, C = CT ? CT : a.C;
     const int nt = a.ntx * a.ntx;
-    const int count = a.tile_list ? a.tile_list[0] : a.B * nt;
+    TileList tl;
+    if (a.tile_list) tl = open_tile_list(a.tile_list, a.B * nt);
+    const int count = a.tile_list ? tl.total : a.B * nt;
     for (int work = blockIdx.x; work < count; work += gridDim.x) {
     int b, tx, ty;
     if (a.tile_list) {
-        const int4 e = __ldg(reinterpret_cast<const int4 *>(a.tile_list + TILE_LIST_HDR) + work);
+        const int4 e = tile_entry(tl, work);
         b = e.x; tx = e.y & 0xffff; ty = e.y >> 16;
     } else {
         b = work / nt;

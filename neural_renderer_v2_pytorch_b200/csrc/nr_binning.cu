@@ -153,15 +153,21 @@ k_scan_tiles(const int *__restrict__ tile_count, int *__restrict__ tile_offset,
             tile_offset[(size_t)b * nt + i] = excl;
             tile_cursor[(size_t)b * nt + i] = excl;
         }
-        // append the non-empty tiles to the work list (one atomic per warp)
-        const unsigned busy = __ballot_sync(0xffffffffu, v > 0);
-        if (busy) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&tile_list[0], __popc(busy));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (v > 0) {
-                int4 *ent = reinterpret_cast<int4 *>(tile_list + TILE_LIST_HDR) + base + __popc(busy & ((1u << lane) - 1u));
-                *ent = make_int4(b, (i % ntx) | ((i / ntx) << 16), excl, v);
+        // append the non-empty tiles to the work list of their length class (one atomic per warp and class)
+        const int cls = tile_class(v);
+        const int cap = (int)gridDim.x * nt;
+#pragma unroll
+        for (int k = 0; k < TILE_CLASSES; ++k) {
+            const unsigned busy = __ballot_sync(0xffffffffu, v > 0 && cls == k);
+            if (busy) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&tile_list[k], __popc(busy));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (v > 0 && cls == k) {
+                    int4 *ent = reinterpret_cast<int4 *>(tile_list + TILE_LIST_HDR) + (size_t)k * cap + base +
+                                __popc(busy & ((1u << lane) - 1u));
+                    *ent = make_int4(b, (i % ntx) | ((i / ntx) << 16), excl, v);
+                }
             }
         }
         carry += s_warp[31];
@@ -198,20 +204,20 @@ constexpr int SORT_WARPS = 8;
 constexpr int SORT_PER_LANE = 4;
 constexpr int SORT_WARP_MAX = 32 * SORT_PER_LANE;     // lists up to this length: one warp each
 __global__ void __launch_bounds__(SORT_WARPS * 32)
-k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
+k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict__ pairs,
              const BinHeader *__restrict__ hdr) {
     __shared__ int s_ids[SMEM_SORT_CAP];
     __shared__ int s_long[SORT_WARPS * 32];
     __shared__ int s_nlong;
     if (hdr->overflow) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int count = tile_list[0];
-    const int4 *entries = reinterpret_cast<const int4 *>(tile_list + TILE_LIST_HDR);
+    const TileList tl = open_tile_list(tile_list, cap);
+    const int count = tl.total;
 
     // ---- pass A: lists of up to 128 ids, one warp per list, ids held in registers
     // (position p of the list lives in register p / 32 of lane p % 32)
     for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
-        const int4 e = entries[w];
+        const int4 e = tile_entry(tl, w);
         const int n = e.w;
         if (n < 2 || n > SORT_WARP_MAX) continue;
         int32_t *a = pairs + e.z;
@@ -256,13 +262,13 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int32_t *__restrict__ pairs,
         __syncthreads();
         const int w = (base + tid) * (int)gridDim.x + (int)blockIdx.x;
         if (w < count) {
-            const int n = entries[w].w;
+            const int n = tile_entry(tl, w).w;
             if (n > SORT_WARP_MAX && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
         }
         __syncthreads();
         const int nlong = s_nlong;
         for (int li = 0; li < nlong; ++li) {
-            const int4 e = entries[s_long[li]];
+            const int4 e = tile_entry(tl, s_long[li]);
             const int n = e.w;
             int32_t *a = pairs + e.z;
             int unsorted = 0;
@@ -379,7 +385,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
                                                   a.pair_capacity, a.hdr);
         }
         ProfScope p(PROF_SORT_LONG, stream);
-        k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.pairs, a.hdr);
+        k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
         k_sort_long<<<a.sm_count * 2, 256, 0, stream>>>(a.tile_count, a.tile_offset, a.B * nt, a.pairs,
                                                         SMEM_SORT_CAP, a.hdr);
     }

@@ -30,11 +30,45 @@ struct BinHeader {
     int pad[59];
 };
 
-// Non-empty tiles of one forward call, consumed by the raster kernel and again by the backward:
-//   list[0] = number of entries; entry i = 4 ints at list[TILE_LIST_HDR + 4 i]:
+// Non-empty tiles of one forward call, consumed by the raster kernel and again by the backward.
+// The tiles are kept in TILE_CLASSES regions by list length, longest lists first, so that the
+// dynamically scheduled raster kernel starts with the expensive tiles and ends with cheap ones:
+//   list[k], k < TILE_CLASSES = number of entries of class k
+//   entry i of class k = 4 ints at list[TILE_LIST_HDR + 4 (k cap + i)], cap = views * tiles_per_view:
 //   (view, tile_x | tile_y << 16, offset of the tile's face list in the pair array, its length)
-constexpr int TILE_LIST_HDR = 4;
+constexpr int TILE_LIST_HDR = 8;
 constexpr int TILE_ENTRY_INTS = 4;
+constexpr int TILE_CLASSES = 4;
+__host__ __device__ inline int tile_class(int n) { return n > 96 ? 0 : (n > 48 ? 1 : (n > 24 ? 2 : 3)); }
+
+struct TileList {
+    const int4 *entries;
+    int cap, total;
+    int c[TILE_CLASSES];
+};
+__device__ __forceinline__ TileList open_tile_list(const int32_t *list, int cap) {
+    TileList t;
+    t.entries = reinterpret_cast<const int4 *>(list + TILE_LIST_HDR);
+    t.cap = cap;
+    t.total = 0;
+#pragma unroll
+    for (int k = 0; k < TILE_CLASSES; ++k) {
+        t.c[k] = list[k];
+        t.total += t.c[k];
+    }
+    return t;
+}
+// i-th tile in heavy-first order
+__device__ __forceinline__ int4 tile_entry(const TileList &t, int i) {
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < TILE_CLASSES - 1; ++j)
+        if (k == j && i >= t.c[j]) {
+            i -= t.c[j];
+            ++k;
+        }
+    return __ldg(t.entries + (size_t)k * t.cap + i);
+}
 static_assert(sizeof(BinHeader) == 256, "header is one 256-byte block");
 
 // Per (view, face) record written by the setup kernel: 48 bytes, three float4 loads.

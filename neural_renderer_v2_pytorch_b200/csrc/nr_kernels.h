@@ -30,7 +30,7 @@ struct BinningArgs {
     int32_t *pairs;
     long long pair_capacity;
     BinHeader *hdr;
-    int32_t *tile_list;     // [TILE_LIST_HDR + B * ntx * ntx], zeroed here
+    int32_t *tile_list;     // [TILE_LIST_HDR + 4 * TILE_CLASSES * B * ntx * ntx] ints, header zeroed here
     int sm_count;
 };
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);

@@ -102,9 +102,8 @@ k_raster(const RasterArgs a) {
     const bool overflow = a.hdr->overflow != 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int R = a.R;
-    const int count = a.tile_list[0];
-    const int4 *entries = reinterpret_cast<const int4 *>(a.tile_list + TILE_LIST_HDR);
-    const int items = count * RASTER_WARPS;
+    const TileList tl = open_tile_list(a.tile_list, a.B * a.ntx * a.ntx);
+    const int items = tl.total * RASTER_WARPS;
     const bool aa = (a.flags & FLAG_AA) != 0;
     const bool pow2 = (R & (R - 1)) == 0;
     const float invR = 1.f / (float)R;          // exact for power-of-two R
@@ -114,7 +113,7 @@ k_raster(const RasterArgs a) {
 
     // dynamic scheduling: a warp claims two adjacent blocks at a time; the next claim is issued
     // before the current pair is processed so its latency is hidden
-    constexpr int GRAB = 2;
+    constexpr int GRAB = 1;
     int claim = 0;
     if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
     while (true) {
@@ -122,7 +121,7 @@ k_raster(const RasterArgs a) {
         if (first >= items) break;
         if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
     for (int item = first; item < min(first + GRAB, items); ++item) {
-        const int4 e0 = __ldg(entries + (item >> 3));
+        const int4 e0 = tile_entry(tl, item >> 3);
         const int sub = item & 7;
         const int b = e0.x, n = overflow ? a.nf : e0.w;
         const int32_t *list = a.pairs + e0.z;

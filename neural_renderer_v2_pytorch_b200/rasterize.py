@@ -148,7 +148,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None):
         wmap = torch.empty((B, R, R, 3), dtype=torch.float32, device=dev) if want_maps else None
         dmap = torch.empty((B, R, R), dtype=torch.float32, device=dev) if want_maps else None
         ntx = (R + 15) // 16
-        tile_list = torch.empty(4 + 4 * B * ntx * ntx, dtype=torch.int32, device=dev)
+        tile_list = torch.empty(8 + 16 * B * ntx * ntx, dtype=torch.int32, device=dev)
         capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
         if FORCE_PAIR_CAPACITY is not None:
             capacity = int(FORCE_PAIR_CAPACITY)
