@@ -353,6 +353,55 @@ def test_no_faces_and_double_precision_inputs(nr):
     grad_close(v64.grad.cpu().numpy(), d["grad_vertices"], "grad_vertices (float64 input)")
 
 
+def test_interleaved_forwards_and_repeated_backward(nr):
+    """Two forwards share the cached workspace before either backward runs; backward twice through the
+    same graph (retain_graph) gives the same gradient (everything the backward needs is saved per call)."""
+    d1 = np.load(os.path.join(GOLDEN, "case_rgba_64.npz"))
+    d2 = np.load(os.path.join(GOLDEN, "case_sil_cull_64.npz"))
+    dev = "cuda:0"
+    v1 = torch.from_numpy(d1["vertices"]).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(d1["textures"]).to(dev).requires_grad_(True)
+    p1 = nr.RasterizeParam(vertices_textures=torch.from_numpy(d1["vertices_textures"]).to(dev),
+                           faces_textures=torch.from_numpy(d1["faces_textures"]).to(dev), textures=tex)
+    i1 = nr.rasterize_rgba(v1, torch.from_numpy(d1["faces"]).to(dev), p1, nr.RasterizeHyperparam(image_size=64, anti_aliasing=False))
+    v2 = torch.from_numpy(d2["vertices"]).to(dev).requires_grad_(True)
+    i2 = nr.rasterize_silhouettes(v2, torch.from_numpy(d2["faces"]).to(dev), nr.RasterizeParam(),
+                                  nr.RasterizeHyperparam(image_size=64, anti_aliasing=False, draw_backside=False))
+    loss = (i1 * torch.from_numpy(d1["grad_images"]).to(dev)).sum() + (i2 * torch.from_numpy(d2["grad_images"]).to(dev)).sum()
+    loss.backward(retain_graph=True)
+    grad_close(v1.grad.cpu().numpy(), d1["grad_vertices"], "grad_vertices of the first render")
+    grad_close(v2.grad.cpu().numpy(), d2["grad_vertices"], "grad_vertices of the second render")
+    grad_close(tex.grad.cpu().numpy(), d1["grad_textures"], "grad_textures")
+    loss.backward()                               # accumulates: exactly twice the gradient
+    grad_close(v1.grad.cpu().numpy() / 2, d1["grad_vertices"], "second backward through the same graph")
+
+
+def test_capture_step_replays_the_whole_step(nr):
+    """nr.capture_step: a CUDA-graph replay recomputes forward + backward on the current contents of
+    the static inputs."""
+    d = np.load(os.path.join(GOLDEN, "case_sil_64.npz"))
+    dev = "cuda:0"
+    v = torch.from_numpy(d["vertices"]).to(dev).requires_grad_(True)
+    faces = torch.from_numpy(d["faces"]).to(dev)
+    G = torch.from_numpy(d["grad_images"]).to(dev)
+
+    def step():
+        img = nr.rasterize_silhouettes(v, faces, nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=64, anti_aliasing=False))
+        img.backward(G)
+        return img
+
+    replay = nr.capture_step(step, params=[v], warmup=2)
+    img = replay()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(img.detach().cpu().numpy(), d["images"], atol=1e-6)
+    grad_close(v.grad.cpu().numpy(), d["grad_vertices"], "replayed gradient")
+    with torch.no_grad():
+        v.mul_(0.5)                               # new input in the same static buffer
+    img2 = replay().detach().clone()
+    want = nr.rasterize_silhouettes(v.detach(), faces, nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=64, anti_aliasing=False))
+    assert torch.equal(img2, want)
+
+
 def test_fused_matches_oracle_pipeline_midsize(nr):
     """Fused forward + backward vs the torch-CPU oracle at 128^2, RGBA + depth in one call."""
     d = np.load(os.path.join(GOLDEN, "teapot.npz"))
