@@ -12,8 +12,8 @@
 //                   counts the face into every 16x16 tile its pixel box touches.
 //   k_scan_tiles  : exclusive prefix sum of the per-tile counts (one CTA per view).
 //   k_scatter     : writes face ids into the tile segments (slot order is arbitrary ...)
-//   k_sort_tiles  : ... so every list is sorted in place (one warp per list, most are already
-//   k_sort_long     in order); lists longer than SMEM_SORT_CAP go through k_sort_long.
+//   k_sort_tiles  : ... so every list is sorted in place: <= 128 ids by one warp in registers,
+//                   <= 8192 by a CTA in shared memory, longer ones by a CTA in global memory.
 #include "nr_kernels.h"
 
 namespace nr {
@@ -310,25 +310,23 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
         }
         __syncthreads();
     }
-}
 
-// Ascending in-place sort of the segments that are too long for the shared-memory sort.  Same-direction bitonic network over a virtual power-of-two length
-// (indices >= n behave as +inf and never move), one CTA per long segment, grid-stride over tiles.
-__global__ void __launch_bounds__(256)
-k_sort_long(const int *__restrict__ tile_count, const int *__restrict__ tile_offset, int total_tiles,
-            int32_t *__restrict__ pairs, int threshold, const BinHeader *__restrict__ hdr) {
-    if (hdr->overflow || hdr->max_tile_faces <= threshold) return;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n = tile_count[t];
-        if (n <= threshold) continue;
-        int32_t *a = pairs + tile_offset[t];
-        int np2 = 1;
-        while (np2 < n) np2 <<= 1;
-        for (int k = 2; k <= np2; k <<= 1) {
-            // first stage of the merge: compare i with its mirror inside the k-block
-            for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
-                const int blk = i / (k / 2), off = i % (k / 2);
-                const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+    // ---- pass C (rare): lists longer than the shared-memory capacity, sorted in place in global
+    // memory with the same network, one CTA per list
+    if (hdr->max_tile_faces <= SMEM_SORT_CAP) return;
+    for (int w = blockIdx.x; w < count; w += gridDim.x) {
+        const int4 e = tile_entry(tl, w);
+        const int n = e.w;
+        if (n <= SMEM_SORT_CAP) continue;
+        int32_t *a = pairs + e.z;
+        int lg = 1;
+        while ((1 << lg) < n) ++lg;
+        const int half = 1 << (lg - 1);
+        for (int kk = 1; kk <= lg; ++kk) {
+            const int k = 1 << kk;
+            for (int i = tid; i < half; i += blockDim.x) {
+                const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
+                const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
                 if (hi < n) {
                     const int x = a[lo], y = a[hi];
                     if (x > y) {
@@ -338,9 +336,10 @@ k_sort_long(const int *__restrict__ tile_count, const int *__restrict__ tile_off
                 }
             }
             __syncthreads();
-            for (int j = k / 4; j >= 1; j >>= 1) {
-                for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
-                    const int lo = (i / j) * 2 * j + (i % j), hi = lo + j;
+            for (int jj = kk - 2; jj >= 0; --jj) {
+                const int j = 1 << jj;
+                for (int i = tid; i < half; i += blockDim.x) {
+                    const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
                     if (hi < n) {
                         const int x = a[lo], y = a[hi];
                         if (x > y) {
@@ -386,8 +385,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
         }
         ProfScope p(PROF_SORT_LONG, stream);
         k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
-        k_sort_long<<<a.sm_count * 2, 256, 0, stream>>>(a.tile_count, a.tile_offset, a.B * nt, a.pairs,
-                                                        SMEM_SORT_CAP, a.hdr);
+
     }
     return cudaGetLastError();
 }
