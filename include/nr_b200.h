@@ -74,7 +74,8 @@ typedef struct nrRasterConfig {
 } nrRasterConfig;
 
 /*
- * Optional shading (rasterize.py:252-283 with the smooth normal map of :162-190); NULL = unlit.
+ * Optional shading inputs; NULL = unlit, black background.
+ * Lights (rasterize.py:252-283 with the smooth normal map of :162-190), num_lights = 0 for none.
  * Light l of view b is data[(l * B + b) * 8 ..]: colour rgb, direction xyz, alpha, unused.
  * types[l]: 0 ambient (lights.py:22-24), 1 directional (:10-19), 2 specular (:27-39); +4 = backside
  * (|intensity| instead of relu).  vertex_normals [B, nv, 3] are the normalised per-vertex normals
@@ -87,6 +88,11 @@ typedef struct nrLights {
     const float *data;           /* [L, B, 8] */
     const float *vertex_normals; /* [B, nv, 3] */
     float *grad_vertex_normals;  /* backward only, may be NULL */
+    /* Backgrounds [B, 3, R, R] at INTERNAL resolution, in output orientation: behind every background
+     * pixel the rgb channels show backgrounds[b, :, Y, X] (2x2-averaged under anti-aliasing).  This is
+     * what rasterize.py:156-159 intends (it fails on torch tensors); semantics follow the Chainer
+     * original, neural_renderer_chainer/rasterize.py:574-577.  NULL = black. */
+    const float *backgrounds;
 } nrLights;
 
 /*

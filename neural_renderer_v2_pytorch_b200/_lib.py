@@ -50,7 +50,8 @@ class RasterConfig(ctypes.Structure):
 class Lights(ctypes.Structure):
     """``nrLights``."""
     _fields_ = [("num_lights", ctypes.c_int32), ("types", ctypes.c_void_p), ("data", ctypes.c_void_p),
-                ("vertex_normals", ctypes.c_void_p), ("grad_vertex_normals", ctypes.c_void_p)]
+                ("vertex_normals", ctypes.c_void_p), ("grad_vertex_normals", ctypes.c_void_p),
+                ("backgrounds", ctypes.c_void_p)]
 
 
 class BinStats(ctypes.Structure):

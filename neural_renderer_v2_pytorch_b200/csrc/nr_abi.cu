@@ -245,12 +245,13 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.internal = images_internal;
     ra.faces = faces;
     ra.nv = cfg->num_vertices;
-    ra.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr};
+    ra.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (lights && lights->num_lights > 0 && rgb) {
         if (!lights->types || !lights->data || !lights->vertex_normals)
             return fail(NR_ERR_INVALID_ARGUMENT, "lights: types, data and vertex_normals are required");
-        ra.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals, nullptr};
+        ra.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals, nullptr, nullptr};
     }
+    if (lights && rgb) ra.lights.backgrounds = lights->backgrounds;
 
     // fork: background fill on the side stream, binning on the caller's stream
     cudaError_t e;
@@ -308,12 +309,12 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
     a.grad_verts = grad_vertices;
     a.grad_tex = grad_textures;
     a.grad_vt = grad_vertices_textures;
-    a.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr};
+    a.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (lights && lights->num_lights > 0 && rgb) {
         if (!lights->types || !lights->data || !lights->vertex_normals)
             return fail(NR_ERR_INVALID_ARGUMENT, "lights: types, data and vertex_normals are required");
         a.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals,
-                                 lights->grad_vertex_normals};
+                                 lights->grad_vertex_normals, nullptr};
     }
     a.det_verts = a.det_tex = a.det_vt = nullptr;
     a.det_scale = 4294967296.f;     // 2^32: resolution 2.3e-10, |sum| < 2.1e9

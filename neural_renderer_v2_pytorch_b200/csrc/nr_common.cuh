@@ -190,6 +190,7 @@ struct LightArgs {
     const float *data;       // [L, B, 8]
     const float *vnormals;   // [B, nv, 3]
     float *grad_vnormals;    // backward
+    const float *backgrounds;   // [B, 3, R, R] output orientation, or null
 };
 
 // Colour weight of one pixel from its interpolated normal n (rasterize.py:256-282), and when

@@ -256,6 +256,9 @@ k_raster(const RasterArgs a) {
             const bool any_fg_quad = aa && __any_sync(0xffffffffu, fg);
             // one channel value of this pixel -> images (and the internal-resolution copy under AA)
             auto put = [&](int c, float val) {
+                // background pixels of a partly covered 2x2 quad contribute the background colour
+                if (aa && !fg && valid && c < 3 && (a.flags & FLAG_RGB) && a.lights.backgrounds)
+                    val = __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * R + u_) * R + v_);
                 if (!aa) {
                     if (fg) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
                     return;
@@ -339,6 +342,18 @@ k_weight_map_compat(const float *__restrict__ faces, const int32_t *__restrict__
     wmap[i * 3 + 2] = w2;
 }
 
+// 2x2 mean of the background picture (rasterize.py:321-328 applied to a pure-background image)
+__global__ void __launch_bounds__(256)
+k_background_downsample(const float *__restrict__ bg, float *__restrict__ images, int B, int C, int S) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * 3 * S * S) return;
+    const int X = (int)(i % S), Y = (int)((i / S) % S), c = (int)((i / ((long long)S * S)) % 3), b = (int)(i / ((long long)3 * S * S));
+    const int R = 2 * S;
+    const float *p = bg + (((size_t)b * 3 + c) * R + 2 * Y) * R + 2 * X;
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[R]), p[1]), p[R + 1]);
+    images[(((size_t)b * C + c) * S + Y) * S + X] = __fmul_rn(sum, 0.25f);
+}
+
 // Background everywhere (face index -1, zeros elsewhere); the raster kernel then writes foreground
 // pixels only.  Independent of the binning kernels, so the caller runs it on a side stream.
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream) {
@@ -351,6 +366,19 @@ cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream) {
     if (e == cudaSuccess && a.images)
         e = cudaMemsetAsync(a.images, 0, (size_t)a.B * a.C * a.S * a.S * sizeof(float), stream);
     if (e == cudaSuccess && a.images && a.internal) e = cudaMemsetAsync(a.internal, 0, P * a.C * sizeof(float), stream);
+    if (e == cudaSuccess && a.images && a.lights.backgrounds && (a.flags & FLAG_RGB)) {
+        // rgb planes (the first three of every view) start as the background picture
+        const size_t row = (size_t)3 * a.R * a.R * sizeof(float);
+        float *dst = a.internal ? a.internal : a.images;       // internal resolution
+        e = cudaMemcpy2DAsync(dst, (size_t)a.C * a.R * a.R * sizeof(float), a.lights.backgrounds, row, row, a.B,
+                              cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess && a.internal) {
+            const long long n = (long long)a.B * 3 * a.S * a.S;
+            k_background_downsample<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a.lights.backgrounds, a.images, a.B,
+                                                                                    a.C, a.S);
+            e = cudaGetLastError();
+        }
+    }
     return e;
 }
 

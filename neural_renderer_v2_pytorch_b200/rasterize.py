@@ -7,8 +7,10 @@ torch ops with per-view host synchronisation.
 Differences from the reference that are deliberate (DESIGN.md "API notes"):
   * ``hyperparams.image_size`` is NOT doubled in place when anti-aliasing is on
     (the reference mutates the caller's object, rasterize.py:227-228);
-  * ``backgrounds`` / ``background_color`` raise ``NotImplementedError`` (broken in the reference,
-    rasterize.py:156-159: ``.astype`` / ``[::-1]`` on tensors).
+  * ``backgrounds`` / ``background_color`` work: the reference's ``blend_backgrounds``
+    (rasterize.py:156-159) fails on torch tensors (``.astype`` / ``[::-1]``) and its ``background_color``
+    multiplies a zero tensor (:208-215); here they do what the Chainer original blends
+    (neural_renderer_chainer/rasterize.py:574-577) with a constant colour that is actually the colour.
 """
 import ctypes
 
@@ -115,17 +117,22 @@ def _flags_of(hp):
             (_lib.NR_DETERMINISTIC if (DETERMINISTIC or getattr(hp, "deterministic", False)) else 0))
 
 
-def _lights_struct(lights, grad_vn=None):
-    """lights = (types, data, vertex_normals) or None -> ctypes nrLights pointer or None."""
-    if lights is None:
+def _lights_struct(lights, grad_vn=None, backgrounds=None):
+    """lights = (types, data, vertex_normals) or None, backgrounds [B,3,R,R] or None
+    -> ctypes nrLights pointer or None."""
+    if lights is None and backgrounds is None:
         return None
+    bg = backgrounds.data_ptr() if backgrounds is not None else None
+    if lights is None:
+        return ctypes.byref(_lib.Lights(num_lights=0, backgrounds=bg))
     types, data, vn = lights
     return ctypes.byref(_lib.Lights(num_lights=types.shape[0], types=types.data_ptr(), data=data.data_ptr(),
                                     vertex_normals=vn.data_ptr(),
-                                    grad_vertex_normals=grad_vn.data_ptr() if grad_vn is not None else None))
+                                    grad_vertex_normals=grad_vn.data_ptr() if grad_vn is not None else None,
+                                    backgrounds=bg))
 
 
-def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None):
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None):
     """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
     Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
@@ -169,7 +176,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None):
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
             ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
             ctypes.c_void_p(sc.stats.data_ptr()) if track else None, sc.event if track else None,
-            _lights_struct(lights), ctypes.c_void_p(stream))
+            _lights_struct(lights, None, backgrounds), ctypes.c_void_p(stream))
         _lib.check(rc, "nr_rasterize_forward")
         if track:
             sc.pending = True
@@ -199,15 +206,18 @@ class _Rasterize(torch.autograd.Function):
     every autograd edge the reference has on this path)."""
 
     @staticmethod
-    def forward(ctx, vertices, vertices_textures, textures, vertex_normals, faces, faces_textures, cfg, light_pack):
+    def forward(ctx, vertices, vertices_textures, textures, vertex_normals, backgrounds, faces, faces_textures, cfg,
+                light_pack):
         v = _f32c(vertices)
+        bg = _f32c(backgrounds) if backgrounds is not None else None
         vt = _f32c(vertices_textures) if vertices_textures is not None else None
         tex = _f32c(textures) if textures is not None else None
         lights = None
         if light_pack is not None:
             lights = (light_pack[0], light_pack[1], _f32c(vertex_normals))
-        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights)
+        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg)
         ctx.cfg = cfg
+        ctx.bg_dtype = backgrounds.dtype if backgrounds is not None else None
         ctx.has_tex = tex is not None
         ctx.has_lights = lights is not None
         ctx.in_dtypes = tuple(t.dtype if t is not None else None for t in (vertices, vertices_textures, textures, vertex_normals))
@@ -234,6 +244,14 @@ class _Rasterize(torch.autograd.Function):
             vt = ft = tex = None
         g = _f32c(grad_images)
         need_v, need_vt, need_tex = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gbg = None
+        if ctx.bg_dtype is not None and ctx.needs_input_grad[4]:
+            # blend backward: background pixels pass the rgb gradient straight to the picture
+            # (output orientation = flipped internal orientation; 2x2 mean backward under AA)
+            grgb = g[:, :3]
+            if cfg.flags & _lib.NR_ANTI_ALIASING:
+                grgb = (grgb * 0.25).repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+            gbg = (grgb * (torch.flip(fim, dims=(1, 2)) < 0)[:, None]).to(ctx.bg_dtype)
         dev = v.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -251,7 +269,8 @@ class _Rasterize(torch.autograd.Function):
             _lib.check(rc, "nr_rasterize_backward")
         cast = lambda g_, dt: g_.to(dt) if (g_ is not None and dt is not None and g_.dtype != dt) else g_
         dv, dvt, dtex, dvn = ctx.in_dtypes
-        return (cast(gv, dv) if need_v else None), cast(gvt, dvt), cast(gtex, dtex), cast(gvn, dvn), None, None, None, None
+        return ((cast(gv, dv) if need_v else None), cast(gvt, dvt), cast(gtex, dtex), cast(gvn, dvn), gbg,
+                None, None, None, None)
 
 
 def _prepare(vertices, faces, params, hyperparams):
@@ -260,11 +279,24 @@ def _prepare(vertices, faces, params, hyperparams):
     assert vertices.shape[2] == 3
     assert faces.ndim == 2
     assert faces.shape[1] == 3
-    _require_cuda(vertices, "vertices")
-    if params.backgrounds is not None or params.background_color is not None:
-        raise NotImplementedError("backgrounds are outside the accelerated path (and broken in the "
-                                  "reference, rasterize.py:156-159)")
     dev = vertices.device
+    bg = None
+    if hyperparams.draw_rgb:
+        # rasterize.py:207-225; backgrounds only ever touch the rgb channels (:286-288)
+        R_ = int(hyperparams.image_size) * (2 if hyperparams.anti_aliasing else 1)
+        if params.background_color is not None:
+            color = torch.as_tensor(params.background_color, dtype=torch.float32, device=dev)
+            assert color.shape == (3,)
+            bg = color[None, :, None, None].expand(vertices.shape[0], 3, R_, R_)
+        elif params.backgrounds is not None:
+            bg = params.backgrounds
+            assert bg.ndim == 4
+            assert bg.shape[0] == vertices.shape[0]
+            assert bg.shape[1] == 3
+            assert bg.shape[2] == R_
+            assert bg.shape[3] == R_
+            _require_cuda(bg, "backgrounds")
+    _require_cuda(vertices, "vertices")
     faces = torch.as_tensor(faces)
     faces_d = _i32c(faces).to(dev)
     B, nv = vertices.shape[:2]
@@ -294,24 +326,25 @@ def _prepare(vertices, faces, params, hyperparams):
         # shading: per-vertex normals by differentiable torch ops (O(nv + nf)), the per-pixel part in the kernels
         light_pack = light_lib.pack_lights(params.lights, B, dev)
         vn = light_lib.vertex_normals(vertices, faces_d)
-    return cfg, faces_d, vt, ft, tex, vn, light_pack
+    return cfg, faces_d, vt, ft, tex, vn, light_pack, bg
 
 
 def rasterize_core(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
     """``rasterize.py:194-329``. vertices [B,nv,3] screen space, faces [nf,3] -> images [B,C,S,S]."""
-    cfg, faces_d, vt, ft, tex, vn, light_pack = _prepare(vertices, faces, params, hyperparams)
-    return _Rasterize.apply(vertices, vt, tex, vn, faces_d, ft, cfg, light_pack)
+    cfg, faces_d, vt, ft, tex, vn, light_pack, bg = _prepare(vertices, faces, params, hyperparams)
+    return _Rasterize.apply(vertices, vt, tex, vn, bg, faces_d, ft, cfg, light_pack)
 
 
 def rasterize_maps(vertices, faces, params: RasterizeParam, hyperparams: RasterizeHyperparam):
     """Non-differentiable view of the internal maps the reference builds inside rasterize_core
     (``face_index_map`` :235, ``weight_map`` :236, depth :292) plus the images.  Test / debug aid."""
-    cfg, faces_d, vt, ft, tex, vn, light_pack = _prepare(vertices, faces, params, hyperparams)
+    cfg, faces_d, vt, ft, tex, vn, light_pack, bg = _prepare(vertices, faces, params, hyperparams)
     with torch.no_grad():
         images, internal, fim, wmap, dmap, _ = _forward_call(
             cfg, _f32c(vertices), faces_d, _f32c(vt) if vt is not None else None, ft,
             _f32c(tex) if tex is not None else None, True,
-            (light_pack[0], light_pack[1], _f32c(vn)) if light_pack is not None else None)
+            (light_pack[0], light_pack[1], _f32c(vn)) if light_pack is not None else None,
+            _f32c(bg) if bg is not None else None)
     return dict(images=images, internal_images=internal if internal is not None else images,
                 face_index_map=fim, weight_map=wmap, depth_map=dmap)
 

@@ -182,8 +182,12 @@ def light_color_weights(normal_map, lights):
 
 def rasterize(vertices, faces, image_size, anti_aliasing, near=0.1, far=100.0, eps=1e-5,
               draw_backside=True, draw_rgb=False, draw_silhouettes=True, draw_depth=False,
-              vertices_textures=None, faces_textures=None, textures=None, lights=None, return_maps=False):
-    """``rasterize.py:194-329`` (``rasterize_core``) without lights / backgrounds.
+              vertices_textures=None, faces_textures=None, textures=None, lights=None, backgrounds=None,
+              return_maps=False):
+    """``rasterize.py:194-329`` (``rasterize_core``).  ``backgrounds`` [B,3,R,R] follows what
+    ``blend_backgrounds`` (``rasterize.py:156-159``) is meant to do: that function fails on torch tensors
+    (``.astype``, ``[::-1]``), so this restates the Chainer original it was ported from
+    (``neural_renderer_chainer/rasterize.py:574-577, 722-725``) -- no reference output exists to pin it.
 
     vertices [B,nv,3] screen space (may require grad), faces [nf,3] int.
     Returns images [B,C,S,S] (and the internal maps when ``return_maps``)."""
@@ -203,6 +207,9 @@ def rasterize(vertices, faces, image_size, anti_aliasing, near=0.1, far=100.0, e
         rgb = sample_textures(fv, ft, textures, fim, wmap, eps)
         if lights is not None:
             rgb = rgb * light_color_weights(compute_normal_map(vertices, fidx, fv, fim, wmap), lights)
+        if backgrounds is not None:
+            fg = (0 <= fim).to(torch.float32)[..., None]
+            rgb = fg * rgb + (1 - fg) * torch.flip(backgrounds.permute(0, 2, 3, 1), dims=(1, 2))
         chans.append(rgb)
     if draw_silhouettes:
         chans.append((0 <= fim).to(torch.float32)[..., None])

@@ -435,6 +435,57 @@ def test_fused_matches_oracle_pipeline_midsize(nr):
     grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
 
 
+@pytest.mark.parametrize("aa,mode", [(False, "picture"), (True, "picture"), (True, "color")])
+def test_backgrounds(nr, aa, mode):
+    """Backgrounds.  The reference's blend_backgrounds fails on torch tensors
+    (rasterize.py:156-159), so the oracle restates the Chainer original: no reference output pins this
+    ("parity unpinned").  Checks images, and gradients to vertices (the stencil sees the background
+    colours at silhouette edges), textures and the background picture itself."""
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    B, S, ts = 2, 48, 2
+    R = 2 * S if aa else S
+    g = torch.Generator().manual_seed(7)
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20,
+                                    torch.rand(B, generator=g) * 360)
+    vs = nr.perspective(nr.look_at(vw, eye))
+    faces = torch.from_numpy(d["faces"])
+    vt_np, ft_np, tex_np = nr.create_textures(faces.shape[0], ts)
+    tex0 = torch.rand((B,) + tex_np.shape, generator=g)
+    vt0 = torch.from_numpy(vt_np)[None].repeat(B, 1, 1)
+    G = torch.randn((B, 4, S, S), generator=g)
+    color = [0.25, 0.5, 0.75]
+    if mode == "picture":
+        bg0 = torch.rand((B, 3, R, R), generator=g)
+    else:
+        bg0 = torch.tensor(color)[None, :, None, None].expand(B, 3, R, R).contiguous()
+
+    v0 = vs.clone().requires_grad_(True)
+    t0 = tex0.clone().requires_grad_(True)
+    b0 = bg0.clone().requires_grad_(True)
+    img0 = ref.rasterize(v0, faces, S, aa, draw_rgb=True, draw_silhouettes=True, vertices_textures=vt0,
+                         faces_textures=ft_np, textures=t0, backgrounds=b0)
+    (img0 * G).sum().backward()
+
+    v1 = vs.clone().cuda().requires_grad_(True)
+    t1 = tex0.clone().cuda().requires_grad_(True)
+    b1 = bg0.clone().cuda().requires_grad_(True)
+    hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=aa)
+    kw = dict(backgrounds=b1) if mode == "picture" else dict(background_color=color)
+    p = nr.RasterizeParam(vertices_textures=vt0.cuda(), faces_textures=torch.from_numpy(ft_np).cuda(), textures=t1, **kw)
+    img1 = nr.rasterize_rgba(v1, faces.cuda(), p, hp)
+    (img1 * G.cuda()).sum().backward()
+    assert hp.image_size == S
+    np.testing.assert_allclose(img1.detach().cpu().numpy(), img0.detach().numpy(), rtol=1e-5, atol=1e-6)
+    grad_close(v1.grad.cpu().numpy(), v0.grad.numpy(), "grad_vertices")
+    grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
+    if mode == "picture":
+        grad_close(b1.grad.cpu().numpy(), b0.grad.numpy(), "grad_backgrounds")
+    # silhouettes / depth never see a background (rasterize.py:286-288 is inside the rgb branch)
+    sil = nr.rasterize_silhouettes(v1.detach(), faces.cuda(), p, nr.RasterizeHyperparam(image_size=S, anti_aliasing=aa))
+    assert torch.equal(sil, img1[:, 3].detach())
+
+
 @pytest.mark.parametrize("C", [1, 3, 4])
 def test_differentiation_known_answer(nr, C):
     """Standalone differentiation() op vs the reference's Differentiation.backward output."""

@@ -147,15 +147,19 @@ def test_draw_flags_are_set_like_the_reference():
     assert hp.image_size == 16
 
 
-def test_out_of_scope_features_say_so():
+def test_backgrounds_are_shape_checked_like_the_reference():
+    """rasterize.py:216-225: [B, 3, R, R] with R doubled under anti-aliasing (AssertionError)."""
     from neural_renderer_v2_pytorch_b200.rasterize import _prepare
-    hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=False, draw_rgb=False, draw_depth=False)
     v = torch.zeros(1, 3, 3)
     f = torch.tensor([[0, 1, 2]])
-    for p in (nr.RasterizeParam(background_color=[0, 0, 0]),
-              nr.RasterizeParam(backgrounds=torch.zeros(1, 3, 16, 16))):
-        with pytest.raises((NotImplementedError, RuntimeError)):
-            _prepare(v, f, p, hp)
+    hp = nr.RasterizeHyperparam(image_size=16, anti_aliasing=True, draw_depth=False)
+    for bad in (torch.zeros(1, 3, 16, 16), torch.zeros(2, 3, 32, 32), torch.zeros(1, 4, 32, 32), torch.zeros(3, 32, 32)):
+        with pytest.raises(AssertionError):
+            _prepare(v, f, nr.RasterizeParam(backgrounds=bad), hp)
+    # silhouettes never look at the background (rasterize.py:286-288 sits inside the rgb branch)
+    hp.draw_rgb = False
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        _prepare(v, f, nr.RasterizeParam(backgrounds=torch.zeros(1, 3, 16, 16)), hp)
 
 
 def test_vertex_normals_match_the_dense_incidence_formulation():
