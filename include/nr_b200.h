@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 1
+#define NR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NR_API __attribute__((visibility("default")))
@@ -96,6 +96,19 @@ typedef struct nrLights {
 } nrLights;
 
 /*
+ * Optional buffers the forward zero-fills while it rasterizes: the gradient accumulators of the
+ * coming nr_rasterize_backward (which ADDS into its outputs).  The raster kernel is instruction-issue
+ * bound and leaves HBM idle, so the fill costs nothing there; as a separate fill in front of the
+ * backward it is a serial 30 MB write at BASELINE config 2.  ptr[i] 16-byte aligned, bytes[i] a
+ * multiple of 4.  NULL / count 0 = nothing to fill.
+ */
+typedef struct nrZeroFill {
+    int32_t count;               /* 0..4 */
+    void *ptr[4];
+    size_t bytes[4];
+} nrZeroFill;
+
+/*
  * Written by the forward into the workspace header and, when `stats_host` is given,
  * copied asynchronously to that (pinned) host struct so the caller can look at it once
  * `stats_event` has completed.  overflow != 0 means the (tile, face) pair list did not fit
@@ -140,7 +153,7 @@ NR_API size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg);
 NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity);
 
 /*
- * Fused forward of rasterize_core (rasterize.py:194-329) without lights / backgrounds:
+ * Fused forward of rasterize_core (rasterize.py:194-329); lights / backgrounds through nrLights:
  * face gather (:232), z-buffer (:235), weight map (:236), texture sampling (:249),
  * silhouettes (:242), depth (:292), channel merge (:295-310), permute + flip (:315-316),
  * 2x2 anti-aliasing mean (:321-328).
@@ -168,13 +181,18 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   stats_event         optional cudaEvent_t (as void*, e.g. from nr_event_create) recorded right
  *                       after the stats copy, i.e. BEFORE the raster kernel: waiting on it costs
  *                       the binning kernels only
+ *   zero_fill           optional, see nrZeroFill
+ *
+ * Every element of face_index_map / images / images_internal is written (empty tiles and background
+ * pixels by the raster kernel itself): the caller does not initialise them.
  */
 NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,
                          const float *textures, int32_t *face_index_map, float *weight_map,
                          float *depth_map, float *images, float *images_internal, int32_t *tile_list,
                          void *workspace, size_t workspace_bytes, int64_t pair_capacity,
-                         nrBinStats *stats_host, void *stats_event, const nrLights *lights, void *stream);
+                         nrBinStats *stats_host, void *stats_event, const nrZeroFill *zero_fill,
+                         const nrLights *lights, void *stream);
 
 /*
  * Fused backward: AA / flip / permute backward, the Differentiation stencil

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libnr_b200.so")
 
+ABI_VERSION = 2
 NR_OK = 0
 NR_ERR_INVALID_ARGUMENT = 1
 NR_ERR_CUDA = 2
@@ -52,6 +53,11 @@ class Lights(ctypes.Structure):
     _fields_ = [("num_lights", ctypes.c_int32), ("types", ctypes.c_void_p), ("data", ctypes.c_void_p),
                 ("vertex_normals", ctypes.c_void_p), ("grad_vertex_normals", ctypes.c_void_p),
                 ("backgrounds", ctypes.c_void_p)]
+
+
+class ZeroFill(ctypes.Structure):
+    """``nrZeroFill``."""
+    _fields_ = [("count", ctypes.c_int32), ("ptr", ctypes.c_void_p * 4), ("bytes", ctypes.c_size_t * 4)]
 
 
 class BinStats(ctypes.Structure):
@@ -109,7 +115,8 @@ def lib():
     L.nr_workspace_bytes.argtypes = [ctypes.POINTER(RasterConfig), i64]
     L.nr_rasterize_forward.restype = ctypes.c_int
     L.nr_rasterize_forward.argtypes = [ctypes.POINTER(RasterConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, ctypes.POINTER(Lights), vp]
+                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, ctypes.POINTER(ZeroFill),
+                                       ctypes.POINTER(Lights), vp]
     L.nr_rasterize_backward.restype = ctypes.c_int
     L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 13 + [ctypes.POINTER(Lights), vp]
     L.nr_deterministic_scratch_bytes.restype = ctypes.c_size_t
@@ -130,7 +137,7 @@ def lib():
     L.nr_camera_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
     L.nr_camera_backward.restype = ctypes.c_int
     L.nr_camera_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
-    if L.nr_abi_version() != 1:
+    if L.nr_abi_version() != ABI_VERSION:
         raise RuntimeError("libnr_b200.so ABI version mismatch")
     _lib = L
     return L

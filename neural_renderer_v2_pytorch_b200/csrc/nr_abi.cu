@@ -1,4 +1,5 @@
 // nr_abi.cu -- extern "C" entry points declared in include/nr_b200.h.
+#include <cstdlib>
 #include <stdio.h>
 #include <string.h>
 
@@ -81,32 +82,6 @@ int check_config(const nrRasterConfig *cfg) {
     return NR_OK;
 }
 
-// per-device side stream: the background fill of the outputs does not depend on the binning
-// kernels, so it runs next to them (fork / join with two events) instead of in front of the raster
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-std::mutex g_side_mu;
-SideStream g_side[64];
-
-SideStream *side_stream() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(g_side_mu);
-    SideStream &s = g_side[dev];
-    if (!s.stream) {
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
-            s.stream = nullptr;
-            return nullptr;
-        }
-    }
-    return &s;
-}
-
 // per-device scratch for the two reference-signature operators
 struct CompatScratch {
     void *ptr = nullptr;
@@ -175,7 +150,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
                          const float *textures, int32_t *face_index_map, float *weight_map,
                          float *depth_map, float *images, float *images_internal, int32_t *tile_list,
                          void *workspace, size_t workspace_bytes, int64_t pair_capacity,
-                         nrBinStats *stats_host, void *stats_event, const nrLights *lights, void *stream_) {
+                         nrBinStats *stats_host, void *stats_event, const nrZeroFill *zero_fill,
+                         const nrLights *lights, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool aa = cfg->flags & NR_ANTI_ALIASING, rgb = cfg->flags & NR_DRAW_RGB;
@@ -253,18 +229,20 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     }
     if (lights && rgb) ra.lights.backgrounds = lights->backgrounds;
 
-    // fork: background fill on the side stream, binning on the caller's stream
-    cudaError_t e;
-    SideStream *side = side_stream();
-    if (side) {
-        if ((e = cudaEventRecord(side->fork, stream)) != cudaSuccess) return fail_cuda(e, "fork");
-        if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return fail_cuda(e, "fork wait");
-        if ((e = nr::launch_background_fill(ra, side->stream)) != cudaSuccess) return fail_cuda(e, "background fill");
-        if ((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return fail_cuda(e, "join");
-    } else if ((e = nr::launch_background_fill(ra, stream)) != cudaSuccess) {
-        return fail_cuda(e, "background fill");
+    ra.num_zero = 0;
+    if (zero_fill) {
+        if (zero_fill->count < 0 || zero_fill->count > 4) return fail(NR_ERR_INVALID_ARGUMENT, "zero_fill: count outside 0..4");
+        for (int i = 0; i < zero_fill->count; ++i) {
+            if (!zero_fill->ptr[i] || !zero_fill->bytes[i]) continue;
+            if (((uintptr_t)zero_fill->ptr[i] & 15) || (zero_fill->bytes[i] & 3))
+                return fail(NR_ERR_INVALID_ARGUMENT, "zero_fill: pointer not 16-byte aligned or size not a multiple of 4");
+            ra.zero_ptr[ra.num_zero] = zero_fill->ptr[i];
+            ra.zero_bytes[ra.num_zero++] = zero_fill->bytes[i];
+        }
     }
 
+    cudaError_t e;
+    if ((e = nr::launch_background_fill(ra, stream)) != cudaSuccess) return fail_cuda(e, "map fill");
     e = nr::launch_binning(ba, stream);
     if (e != cudaSuccess) return fail_cuda(e, "binning");
     if (stats_host) {
@@ -275,7 +253,6 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
         e = cudaEventRecord((cudaEvent_t)stats_event, stream);
         if (e != cudaSuccess) return fail_cuda(e, "stats event");
     }
-    if (side && (e = cudaStreamWaitEvent(stream, side->join, 0)) != cudaSuccess) return fail_cuda(e, "join wait");
     e = nr::launch_raster(ra, stream);
     if (e != cudaSuccess) return fail_cuda(e, "raster");
     return NR_OK;
@@ -403,7 +380,8 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
         }
         s.pair_capacity = cap;
         int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
-                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, nullptr, stream);
+                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, nullptr,
+                                      nullptr, stream);
         if (rc != NR_OK) return rc;
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");

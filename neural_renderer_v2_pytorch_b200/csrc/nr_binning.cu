@@ -18,34 +18,28 @@
 
 namespace nr {
 
-__global__ void __launch_bounds__(256)
-k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces, int B, int nv,
-              int nf, int R, int draw_backside, FaceRec *__restrict__ rec,
-              int *__restrict__ tile_count, int ntx, BinHeader *__restrict__ hdr) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)B * nf) return;
-    const int b = (int)(idx / nf), f = (int)(idx % nf);
-
+// Record of face f of one view (vb = that view's vertices) and its exact pixel box; returns false for
+// a face no pixel can accept (its record then carries the dead box).
+__device__ __forceinline__ bool make_face_record(const float *__restrict__ vb, const int32_t *__restrict__ faces,
+                                                 int f, int nv, int R, int draw_backside, FaceRec &r, int &xlo,
+                                                 int &xhi, int &ylo, int &yhi, BinHeader *__restrict__ hdr) {
     int i0, i1, i2;
     if (faces) {
-        i0 = faces[3 * f + 0];
-        i1 = faces[3 * f + 1];
-        i2 = faces[3 * f + 2];
+        i0 = __ldg(faces + 3 * f + 0);
+        i1 = __ldg(faces + 3 * f + 1);
+        i2 = __ldg(faces + 3 * f + 2);
     } else {
         i0 = 3 * f;
         i1 = i0 + 1;
         i2 = i0 + 2;
     }
-    FaceRec r;
     r.q0 = make_float4(0.f, 0.f, 0.f, 0.f);
     r.q1 = r.q0;
     r.q2 = make_float4(0.f, __uint_as_float(DEAD_BBOX), 0.f, 0.f);
     if ((unsigned)i0 >= (unsigned)nv || (unsigned)i1 >= (unsigned)nv || (unsigned)i2 >= (unsigned)nv) {
         hdr->bad_index = 1;
-        rec[idx] = r;
-        return;
+        return false;
     }
-    const float *vb = verts + (size_t)b * nv * 3;
     const float x0 = vb[3 * i0], y0 = vb[3 * i0 + 1], z0 = vb[3 * i0 + 2];
     const float x1 = vb[3 * i1], y1 = vb[3 * i1 + 1], z1 = vb[3 * i1 + 2];
     const float x2 = vb[3 * i2], y2 = vb[3 * i2 + 1], z2 = vb[3 * i2 + 2];
@@ -69,7 +63,7 @@ k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces
                                     __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
         if ((double)fabsf(det) < 0.00000001) alive = false;
     }
-    int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+    xlo = 1; xhi = 0; ylo = 1; yhi = 0;
     if (alive) {
         // :94-97  pixel passes iff  min <= centre <= max  on both axes
         xlo = first_pixel_ge(fminf(x0, fminf(x1, x2)), R);
@@ -82,6 +76,19 @@ k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces
         r.q2.y = __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16));
         r.q2.z = __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16));
     }
+    return alive;
+}
+
+__global__ void __launch_bounds__(256)
+k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces, int B, int nv,
+              int nf, int R, int draw_backside, FaceRec *__restrict__ rec,
+              int *__restrict__ tile_count, int ntx, BinHeader *__restrict__ hdr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * nf) return;
+    const int b = (int)(idx / nf), f = (int)(idx % nf);
+    FaceRec r;
+    int xlo, xhi, ylo, yhi;
+    const bool alive = make_face_record(verts + (size_t)b * nv * 3, faces, f, nv, R, draw_backside, r, xlo, xhi, ylo, yhi, hdr);
     rec[idx] = r;
     if (!alive) return;
 

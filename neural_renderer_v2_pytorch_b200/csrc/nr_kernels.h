@@ -56,6 +56,10 @@ struct RasterArgs {
     const int32_t *faces;   // [nf, 3] vertex ids (null: 3f..3f+2), only read when lights are on
     int nv;
     LightArgs lights;
+    // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
+    int num_zero;
+    void *zero_ptr[4];
+    size_t zero_bytes[4];
 };
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream);
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);

@@ -82,6 +82,67 @@ __device__ __forceinline__ bool block_outside_face(float x0, float y0, float x1,
     return (c2pos && (hi1 < 0.f || hi3 < 0.f)) || (c2neg && (lo1 > 0.f || lo3 > 0.f));
 }
 
+
+// ---- output initialisation, done by the raster kernel itself --------------------------------------
+// The raster kernel is instruction-issue bound and leaves HBM idle, so everything that is a plain
+// fill rides along in it instead of running in front of it: the pixels of EMPTY tiles (face index -1,
+// image 0 or the background picture), and the caller's `zero` buffers (the gradient accumulators of the
+// coming backward).  Pixels of non-empty tiles are all written by the raster items, foreground or not.
+
+// value of rgb channel c behind a background pixel at OUTPUT position (u, v) of view b
+__device__ __forceinline__ float background_value(const RasterArgs &a, int b, int c, int u, int v) {
+    if (!a.lights.backgrounds || c >= 3 || !(a.flags & FLAG_RGB)) return 0.f;
+    return __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * a.R + u) * a.R + v);
+}
+
+__device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane) {
+    const int R = a.R, S = a.S, C = a.C;
+    const bool aa = (a.flags & FLAG_AA) != 0;
+    if ((R & 15) == 0 && !a.lights.backgrounds) {
+        // vector path: a tile row is 64 aligned bytes in every plane; the flipped tile is again a tile
+        const int r = lane >> 2, q = (lane & 3) * 4;
+        const int4 m1 = make_int4(-1, -1, -1, -1);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int y = ty * TILE + r + 8 * h;
+            *reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q) = m1;
+        }
+        if (!a.images) return;
+        const int u0 = R - TILE - ty * TILE, v0 = R - TILE - tx * TILE;
+        float *full = aa ? a.internal : a.images;          // internal-resolution planes
+        for (int c = 0; c < C; ++c) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                *reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q) = z;
+        }
+        if (aa) {
+            for (int i = lane; i < C * 16; i += 32) {
+                const int c = i >> 4, rr = (i >> 1) & 7, hh = (i & 1) * 4;
+                *reinterpret_cast<float4 *>(a.images + (((size_t)b * C + c) * S + (u0 >> 1) + rr) * S + (v0 >> 1) + hh) = z;
+            }
+        }
+        return;
+    }
+    for (int p = lane; p < TILE * TILE; p += 32) {
+        const int xi = tx * TILE + (p & 15), yi = ty * TILE + (p >> 4);
+        if (xi >= R || yi >= R) continue;
+        a.fim[((size_t)b * R + yi) * R + xi] = -1;
+        if (!a.images) continue;
+        const int u = R - 1 - yi, v = R - 1 - xi;
+        float *full = aa ? a.internal : a.images;
+        for (int c = 0; c < C; ++c) {
+            full[(((size_t)b * C + c) * R + u) * R + v] = background_value(a, b, c, u, v);
+            if (aa && !(u & 1) && !(v & 1)) {
+                // rasterize.py:323-328 on a pure-background quad
+                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(background_value(a, b, c, u, v), background_value(a, b, c, u + 1, v)),
+                                                      background_value(a, b, c, u, v + 1)), background_value(a, b, c, u + 1, v + 1));
+                a.images[(((size_t)b * C + c) * S + (u >> 1)) * S + (v >> 1)] = __fmul_rn(sum, 0.25f);
+            }
+        }
+    }
+}
+
 // Persistent kernel over the non-empty tiles.  The unit of work is one WARP = one 8x4 pixel block
 // of a tile (warp-granular static grid-stride; the 8 warps of a CTA take the 8 blocks of one tile, so
 // the tile's records are shared through L1).  Warps never wait for each other: a block without
@@ -111,6 +172,42 @@ k_raster(const RasterArgs a) {
     float4 (*my_rec)[4] = s_rec[wid];
     uint2 *my_bb = s_bb[wid];
 
+    // ---- fill items (stores only), interleaved with the raster items: claim i also performs fill item i,
+    // so the fills drain to HBM all along the kernel instead of in one burst that would stall every warp.
+    // Fill item i < B * tiles: tile i if it is empty; then 4 KB chunks of the caller's zero buffers.
+    constexpr int ZCHUNK = 256;                 // int4 per chunk
+    const int nt = a.ntx * a.ntx, all_tiles = a.B * nt;
+    int zero_chunks[4] = {0, 0, 0, 0}, fill_items = all_tiles;
+    for (int k = 0; k < a.num_zero; ++k) {
+        zero_chunks[k] = (int)((a.zero_bytes[k] >> 4) / ZCHUNK) + 1;      // the last chunk also takes the tail words
+        fill_items += zero_chunks[k];
+    }
+    auto do_fill = [&](int i) {
+        if (i < all_tiles) {
+            if (__ldg(a.tile_count + i) != 0) return;
+            const int b = i / nt, tt = i - b * nt, ty = tt / a.ntx;
+            fill_empty_tile(a, b, tt - ty * a.ntx, ty, lane);
+            return;
+        }
+        int j = i - all_tiles;
+        for (int k = 0; k < a.num_zero; ++k) {
+            if (j >= zero_chunks[k]) {
+                j -= zero_chunks[k];
+                continue;
+            }
+            int4 *dst = reinterpret_cast<int4 *>(a.zero_ptr[k]);
+            const size_t n16 = a.zero_bytes[k] >> 4, base = (size_t)j * ZCHUNK;
+#pragma unroll
+            for (int s = 0; s < ZCHUNK / 32; ++s) {
+                const size_t idx = base + lane + 32 * s;
+                if (idx < n16) dst[idx] = make_int4(0, 0, 0, 0);
+            }
+            if (j == zero_chunks[k] - 1 && lane < (int)((a.zero_bytes[k] & 15) >> 2))
+                reinterpret_cast<int32_t *>(dst + n16)[lane] = 0;
+            return;
+        }
+    };
+
     // dynamic scheduling: a warp claims two adjacent blocks at a time; the next claim is issued
     // before the current pair is processed so its latency is hidden
     constexpr int GRAB = 1;
@@ -118,8 +215,9 @@ k_raster(const RasterArgs a) {
     if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
     while (true) {
         const int first = __shfl_sync(0xffffffffu, claim, 0);
-        if (first >= items) break;
+        if (first >= max(items, fill_items)) break;
         if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
+        if (first < fill_items) do_fill(first);
     for (int item = first; item < min(first + GRAB, items); ++item) {
         const int4 e0 = tile_entry(tl, item >> 3);
         const int sub = item & 7;
@@ -229,9 +327,7 @@ k_raster(const RasterArgs a) {
             }
             __syncwarp();
         }
-        if (__ballot_sync(0xffffffffu, best >= 0) == 0u) continue;   // nothing but background in this block
-
-        // -------------------------------------------------------------- epilogue (foreground only)
+        // ---------------------------------------------- epilogue: every pixel of the block is written
         const bool fg = valid && best >= 0;
         float q[3] = {0.f, 0.f, 0.f};
         if (fg) {
@@ -240,8 +336,8 @@ k_raster(const RasterArgs a) {
         }
         const size_t pix = ((size_t)b * R + yi) * R + xi;
         float dm = 0.f;
+        if (valid) a.fim[pix] = fg ? best : -1;
         if (fg) {
-            a.fim[pix] = best;
             if (a.wmap) {
                 float *w = a.wmap + pix * 3;
                 w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
@@ -253,25 +349,20 @@ k_raster(const RasterArgs a) {
         if (a.images) {
             const int C = a.C, S = a.S;
             const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
-            const bool any_fg_quad = aa && __any_sync(0xffffffffu, fg);
             // one channel value of this pixel -> images (and the internal-resolution copy under AA)
             auto put = [&](int c, float val) {
-                // background pixels of a partly covered 2x2 quad contribute the background colour
-                if (aa && !fg && valid && c < 3 && (a.flags & FLAG_RGB) && a.lights.backgrounds)
-                    val = __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * R + u_) * R + v_);
+                // background pixels show the background picture (black without one)
+                if (!fg && valid) val = background_value(a, b, c, u_, v_);
                 if (!aa) {
-                    if (fg) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
+                    if (valid) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
                     return;
                 }
-                if (!any_fg_quad) return;   // warp-uniform
-                if (fg) a.internal[(((size_t)b * C + c) * R + u_) * R + v_] = val;
+                if (valid) a.internal[(((size_t)b * C + c) * R + u_) * R + v_] = val;
                 // quad in flipped coordinates: F[2Y][2X] is (yi odd, xi odd); rasterize.py:323-328
                 const float px_ = __shfl_xor_sync(0xffffffffu, val, 1);   // same row, other column
                 const float py_ = __shfl_xor_sync(0xffffffffu, val, 8);   // other row, same column
                 const float pd_ = __shfl_xor_sync(0xffffffffu, val, 9);
-                const bool quad_fg = (__shfl_xor_sync(0xffffffffu, (int)fg, 1) | __shfl_xor_sync(0xffffffffu, (int)fg, 8) |
-                                      __shfl_xor_sync(0xffffffffu, (int)fg, 9) | (int)fg) != 0;
-                if (valid && quad_fg && !(xi & 1) && !(yi & 1)) {
+                if (valid && !(xi & 1) && !(yi & 1)) {
                     // me = (even, even) -> F[2Y+1][2X+1]; py_ = (odd row, even col) -> F[2Y][2X+1]
                     // px_ = (even row, odd col) -> F[2Y+1][2X]; pd_ = (odd, odd) -> F[2Y][2X]
                     const float sum = __fadd_rn(__fadd_rn(__fadd_rn(pd_, px_), py_), val);
@@ -342,43 +433,15 @@ k_weight_map_compat(const float *__restrict__ faces, const int32_t *__restrict__
     wmap[i * 3 + 2] = w2;
 }
 
-// 2x2 mean of the background picture (rasterize.py:321-328 applied to a pure-background image)
-__global__ void __launch_bounds__(256)
-k_background_downsample(const float *__restrict__ bg, float *__restrict__ images, int B, int C, int S) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)B * 3 * S * S) return;
-    const int X = (int)(i % S), Y = (int)((i / S) % S), c = (int)((i / ((long long)S * S)) % 3), b = (int)(i / ((long long)3 * S * S));
-    const int R = 2 * S;
-    const float *p = bg + (((size_t)b * 3 + c) * R + 2 * Y) * R + 2 * X;
-    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[R]), p[1]), p[R + 1]);
-    images[(((size_t)b * C + c) * S + Y) * S + X] = __fmul_rn(sum, 0.25f);
-}
-
-// Background everywhere (face index -1, zeros elsewhere); the raster kernel then writes foreground
-// pixels only.  Independent of the binning kernels, so the caller runs it on a side stream.
+// The optional per-pixel maps (weight_map, depth_map: rasterize_maps / the compat operators, not
+// on the hot path) are written for foreground pixels only, so they start as zeros.
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream) {
-    if (a.B <= 0 || a.R <= 0) return cudaSuccess;
+    if (a.B <= 0 || a.R <= 0 || (!a.wmap && !a.dmap)) return cudaSuccess;
     ProfScope p(PROF_MEMSET, stream);
     const size_t P = (size_t)a.B * a.R * a.R;
-    cudaError_t e = cudaMemsetAsync(a.fim, 0xff, P * sizeof(int32_t), stream);   // -1
-    if (e == cudaSuccess && a.wmap) e = cudaMemsetAsync(a.wmap, 0, P * 3 * sizeof(float), stream);
+    cudaError_t e = cudaSuccess;
+    if (a.wmap) e = cudaMemsetAsync(a.wmap, 0, P * 3 * sizeof(float), stream);
     if (e == cudaSuccess && a.dmap) e = cudaMemsetAsync(a.dmap, 0, P * sizeof(float), stream);
-    if (e == cudaSuccess && a.images)
-        e = cudaMemsetAsync(a.images, 0, (size_t)a.B * a.C * a.S * a.S * sizeof(float), stream);
-    if (e == cudaSuccess && a.images && a.internal) e = cudaMemsetAsync(a.internal, 0, P * a.C * sizeof(float), stream);
-    if (e == cudaSuccess && a.images && a.lights.backgrounds && (a.flags & FLAG_RGB)) {
-        // rgb planes (the first three of every view) start as the background picture
-        const size_t row = (size_t)3 * a.R * a.R * sizeof(float);
-        float *dst = a.internal ? a.internal : a.images;       // internal resolution
-        e = cudaMemcpy2DAsync(dst, (size_t)a.C * a.R * a.R * sizeof(float), a.lights.backgrounds, row, row, a.B,
-                              cudaMemcpyDeviceToDevice, stream);
-        if (e == cudaSuccess && a.internal) {
-            const long long n = (long long)a.B * 3 * a.S * a.S;
-            k_background_downsample<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a.lights.backgrounds, a.images, a.B,
-                                                                                    a.C, a.S);
-            e = cudaGetLastError();
-        }
-    }
     return e;
 }
 

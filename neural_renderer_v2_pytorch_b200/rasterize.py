@@ -132,7 +132,19 @@ def _lights_struct(lights, grad_vn=None, backgrounds=None):
                                     backgrounds=bg))
 
 
-def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None):
+def _zero_fill_struct(buffers):
+    """Tensors the forward zero-fills on the side (see nrZeroFill) -> ctypes pointer or None."""
+    buffers = [t for t in buffers if t is not None and t.numel()]
+    if not buffers:
+        return None
+    z = _lib.ZeroFill(count=len(buffers))
+    for i, t in enumerate(buffers):
+        z.ptr[i] = t.data_ptr()
+        z.bytes[i] = t.numel() * t.element_size()
+    return ctypes.byref(z)
+
+
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None, zero=()):
     """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
     Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
@@ -176,7 +188,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
             ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
             ctypes.c_void_p(sc.stats.data_ptr()) if track else None, sc.event if track else None,
-            _lights_struct(lights, None, backgrounds), ctypes.c_void_p(stream))
+            _zero_fill_struct(zero), _lights_struct(lights, None, backgrounds), ctypes.c_void_p(stream))
         _lib.check(rc, "nr_rasterize_forward")
         if track:
             sc.pending = True
@@ -215,7 +227,19 @@ class _Rasterize(torch.autograd.Function):
         lights = None
         if light_pack is not None:
             lights = (light_pack[0], light_pack[1], _f32c(vertex_normals))
-        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg)
+        # The backward ADDS into its outputs.  When a backward is coming its accumulators are allocated
+        # here and zero-filled by the raster kernel on the side (nrZeroFill) instead of by separate
+        # fill kernels in front of the backward.
+        need = ctx.needs_input_grad
+        ctx.grad_bufs = None
+        if any(need[:3]):
+            gv = torch.empty_like(v) if need[0] else None
+            gvt = torch.empty_like(vt) if (need[1] and vt is not None) else None
+            gtex = torch.empty_like(tex) if (need[2] and tex is not None) else None
+            if gv is not None or gvt is not None or gtex is not None:
+                ctx.grad_bufs = (gv, gvt, gtex)
+        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg,
+                                                               ctx.grad_bufs or ())
         ctx.cfg = cfg
         ctx.bg_dtype = backgrounds.dtype if backgrounds is not None else None
         ctx.has_tex = tex is not None
@@ -255,9 +279,11 @@ class _Rasterize(torch.autograd.Function):
         dev = v.device
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            gv = torch.zeros_like(v)
-            gvt = torch.zeros_like(vt) if (need_vt and vt is not None) else None
-            gtex = torch.zeros_like(tex) if (need_tex and tex is not None) else None
+            # accumulators zero-filled by the forward; a repeated backward (retain_graph) makes new ones
+            pre, ctx.grad_bufs = (ctx.grad_bufs or (None, None, None)), None
+            gv = pre[0] if pre[0] is not None else torch.zeros_like(v)
+            gvt = (pre[1] if pre[1] is not None else torch.zeros_like(vt)) if (need_vt and vt is not None) else None
+            gtex = (pre[2] if pre[2] is not None else torch.zeros_like(tex)) if (need_tex and tex is not None) else None
             gvn = torch.zeros_like(lights[2]) if (lights is not None and ctx.needs_input_grad[3]) else None
             scratch = None
             if cfg.flags & _lib.NR_DETERMINISTIC:
