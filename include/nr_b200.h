@@ -56,6 +56,7 @@ enum {
 #define NR_DRAW_BACKSIDE 8    /* rasterize_param.py:20 */
 #define NR_ANTI_ALIASING 16   /* rasterize.py:227-228, 321-328 */
 #define NR_DETERMINISTIC 32   /* backward: fixed-order reduction instead of float atomics */
+#define NR_GENERAL_BINNING 64 /* forward: never take the one-kernel small-mesh binning path (see nrBinStats) */
 
 /* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */
 typedef struct nrRasterConfig {
@@ -119,7 +120,9 @@ typedef struct nrZeroFill {
 typedef struct nrBinStats {
     int32_t total_pairs;      /* sum over tiles of faces whose pixel bbox touches the tile */
     int32_t max_tile_faces;   /* longest per-tile list */
-    int32_t overflow;         /* 1: pair list truncated, results invalid */
+    int32_t overflow;         /* 1: pair list longer than pair_capacity; 2: a view has more pairs than the
+                                 one-kernel small-mesh binning holds in shared memory -> pass
+                                 NR_GENERAL_BINNING from now on.  Results are correct either way. */
     int32_t bad_index;        /* 1: a face referenced a vertex outside [0, nv) (face dropped) */
 } nrBinStats;
 

@@ -88,6 +88,7 @@ struct CompatScratch {
     size_t bytes = 0;
     long long pair_capacity = 0;
     nrBinStats *stats_host = nullptr;
+    int general_faces = -1, general_size = -1;   // this shape outgrew the one-kernel binning (nrBinStats.overflow == 2)
 };
 std::mutex g_compat_mu;
 CompatScratch g_compat[64];
@@ -188,6 +189,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.hdr = c.hdr;
     ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
+    ba.one_cta_per_view = (cfg->flags & NR_GENERAL_BINNING) ? 0 : 1;
 
     nr::RasterArgs ra;
     ra.rec = c.rec;
@@ -367,7 +369,7 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
         if (e != cudaSuccess) return fail_cuda(e, "cudaMallocHost");
     }
     long long cap = s.pair_capacity > 0 ? s.pair_capacity : (long long)batch * num_faces * 4 + 1024;
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         const size_t need = nr_workspace_bytes(&cfg, cap);
         if (need > s.bytes) {
             cudaStreamSynchronize(stream);
@@ -379,6 +381,7 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
             s.bytes = need;
         }
         s.pair_capacity = cap;
+        if (s.general_faces == num_faces && s.general_size == image_size) cfg.flags |= NR_GENERAL_BINNING;
         int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
                                       nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, nullptr,
                                       nullptr, stream);
@@ -386,6 +389,10 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");
         if (!s.stats_host->overflow) return NR_OK;
+        if (s.stats_host->overflow == 2) {
+            s.general_faces = num_faces;
+            s.general_size = image_size;
+        }
         cap = (long long)s.stats_host->total_pairs + 1024;
     }
     return fail(NR_ERR_WORKSPACE_TOO_SMALL, "pair list still overflowing after regrowth");

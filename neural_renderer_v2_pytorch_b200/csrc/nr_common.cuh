@@ -85,27 +85,36 @@ __device__ __forceinline__ float pix_center(int i, int R) {
     return __fdiv_rn((float)(2 * i + 1 - R), (float)R);
 }
 
-// smallest i in [0, R] with pix_center(i) >= v   (R if none)
-__device__ __forceinline__ int first_pixel_ge(float v, int R) {
-    const double t = ((double)v * R + (double)(R - 1)) * 0.5;
-    int i;
-    if (!(t > 0.0)) i = 0;
-    else if (t >= (double)R) i = R;
-    else i = (int)ceil(t);
-    while (i > 0 && pix_center(i - 1, R) >= v) --i;
-    while (i < R && pix_center(i, R) < v) ++i;
+// Pixel-centre coordinates of one resolution.  For a power-of-two R the division is an exact scaling,
+// so a multiplication by 1/R gives the same bits as the reference's division.
+struct PixGrid {
+    int R;
+    float invR;
+    bool pow2;
+    __device__ __forceinline__ explicit PixGrid(int R_) : R(R_), invR(1.f / (float)R_), pow2((R_ & (R_ - 1)) == 0) {}
+    __device__ __forceinline__ float center(int i) const {
+        return pow2 ? __fmul_rn((float)(2 * i + 1 - R), invR) : pix_center(i, R);
+    }
+};
+
+// smallest i in [0, R] with center(i) >= v   (R if none).  The float guess is only a starting point:
+// the two loops make the result exact for any guess (center() is strictly increasing in i).
+__device__ __forceinline__ int first_pixel_ge(float v, const PixGrid &g) {
+    const int R = g.R;
+    const float t = fmaf(v, 0.5f * (float)R, 0.5f * (float)(R - 1));
+    int i = (t > 0.f) ? ((t >= (float)R) ? R : (int)ceilf(t)) : 0;      // NaN -> 0
+    while (i > 0 && g.center(i - 1) >= v) --i;
+    while (i < R && g.center(i) < v) ++i;
     return i;
 }
 
-// largest i in [-1, R-1] with pix_center(i) <= v   (-1 if none)
-__device__ __forceinline__ int last_pixel_le(float v, int R) {
-    const double t = ((double)v * R + (double)(R - 1)) * 0.5;
-    int i;
-    if (!(t >= 0.0)) i = -1;
-    else if (t >= (double)(R - 1)) i = R - 1;
-    else i = (int)floor(t);
-    while (i < R - 1 && pix_center(i + 1, R) <= v) ++i;
-    while (i >= 0 && pix_center(i, R) > v) --i;
+// largest i in [-1, R-1] with center(i) <= v   (-1 if none)
+__device__ __forceinline__ int last_pixel_le(float v, const PixGrid &g) {
+    const int R = g.R;
+    const float t = fmaf(v, 0.5f * (float)R, 0.5f * (float)(R - 1));
+    int i = (t >= 0.f) ? ((t >= (float)(R - 1)) ? R - 1 : (int)floorf(t)) : -1;   // NaN -> -1
+    while (i < R - 1 && g.center(i + 1) <= v) ++i;
+    while (i >= 0 && g.center(i) > v) --i;
     return i;
 }
 

@@ -32,7 +32,9 @@ struct BinningArgs {
     BinHeader *hdr;
     int32_t *tile_list;     // [TILE_LIST_HDR + 4 * TILE_CLASSES * B * ntx * ntx] ints, header zeroed here
     int sm_count;
+    int one_cta_per_view;   // allow the single-kernel small-mesh path (k_bin_view)
 };
+bool binning_fits_one_cta_per_view(int nf, int R);
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
 
 struct RasterArgs {

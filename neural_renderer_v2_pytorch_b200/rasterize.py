@@ -26,6 +26,9 @@ DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
 # RasterizeHyperparam(...).deterministic = True.  Costs one int64 scratch buffer per backward.
 DETERMINISTIC = False
 
+# test hook: always bin with the general multi-kernel path (large meshes) instead of the one-kernel path
+FORCE_GENERAL_BINNING = False
+
 # test hook: force the (tile, face) pair capacity (e.g. 0) to exercise the device-side overflow path
 FORCE_PAIR_CAPACITY = None
 
@@ -66,6 +69,8 @@ class _Scratch:
         self.stats = torch.zeros(4, dtype=torch.int32).pin_memory()
         self.pending = False
         self.overflows = 0
+        self.general_binning = set()        # (nf, R) whose views outgrew the one-kernel small-mesh binning
+        self.last_shape = None
         ev = ctypes.c_void_p()
         _lib.check(_lib.lib().nr_event_create(ctypes.byref(ev)), "nr_event_create")
         self.event = ev
@@ -92,6 +97,8 @@ class _Scratch:
         if overflow:
             self.overflows += 1
             self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
+            if overflow == 2:
+                self.general_binning.add(self.last_shape)
 
     def ensure(self, cfg, capacity):
         need = _lib.lib().nr_workspace_bytes(ctypes.byref(cfg), capacity)
@@ -183,6 +190,10 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         base = ws.data_ptr()
         aligned = (base + 255) & ~255
         track = not sc.pending and not capturing
+        if (cfg.num_faces, R) in sc.general_binning or FORCE_GENERAL_BINNING:
+            cfg.flags |= _lib.NR_GENERAL_BINNING
+        if track:
+            sc.last_shape = (cfg.num_faces, R)
         rc = L.nr_rasterize_forward(
             ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),

@@ -169,7 +169,24 @@ def _check_vs_oracle(nr, faces_np, R, **kw):
     want = oracle.face_index_map(faces_np, R, kw.get("near", 0.1), kw.get("far", 100.0), kw.get("backside", True))
     nbad = int((fim != want).sum())
     assert nbad == 0, "face_index_map: %d / %d pixels differ" % (nbad, fim.size)
-    assert np.array_equal(wm, oracle.weight_map(faces_np, want)), "weight_map differs"
+    want_wm = oracle.weight_map(faces_np, want)
+    assert np.array_equal(wm, want_wm), "weight_map differs"
+    # the fused forward itself, with both binning paths (one kernel per view / general multi-kernel)
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    B, nf = faces_np.shape[:2]
+    v = torch.from_numpy(np.ascontiguousarray(faces_np, dtype=np.float32)).reshape(B, nf * 3, 3).cuda()
+    idx = torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3).cuda()
+    for general in (False, True):
+        rz.FORCE_GENERAL_BINNING = general
+        try:
+            hp = nr.RasterizeHyperparam(image_size=R, near=kw.get("near", 0.1), far=kw.get("far", 100.0), anti_aliasing=False,
+                                        draw_backside=kw.get("backside", True), draw_rgb=False, draw_depth=False)
+            maps = nr.rasterize_maps(v, idx, nr.RasterizeParam(), hp)
+        finally:
+            rz.FORCE_GENERAL_BINNING = False
+        assert np.array_equal(maps["face_index_map"].cpu().numpy(), want), "fused forward (general=%s): face_index_map" % general
+        assert np.array_equal(maps["weight_map"].cpu().numpy(), want_wm), "fused forward (general=%s): weight_map" % general
+        assert np.array_equal(maps["images"][:, 0].flip(1, 2).cpu().numpy(), (want >= 0).astype(np.float32))
     return fim
 
 
@@ -283,6 +300,27 @@ def test_pair_list_overflow_falls_back_on_device(nr):
     assert sc.overflows >= 1 and sc.pair_capacity > 0
     images, v, tex, vt, maps = run_cuda(nr, d)      # regular path again
     assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
+
+
+def test_small_mesh_binning_outgrown_switches_to_the_general_path(nr):
+    """<= 8192 faces take the one-kernel binning (shared-memory pair lists).  200 screen-filling faces at
+    512^2 make ~200k pairs per view, more than it holds: that call must still be exact (device-side
+    fallback) and the host must bin this shape with the general path afterwards."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    f = random_triangles(2, 200, 21, size=1.5)
+    R = 512
+    want = oracle.face_index_map(f, R, 0.1, 100.0, True)
+    v = torch.from_numpy(f).reshape(2, 600, 3).cuda()
+    idx = torch.arange(600, dtype=torch.int32).reshape(200, 3).cuda()
+    sc = rz._Scratch.get(torch.device("cuda", 0), torch.cuda.current_stream().cuda_stream)
+    sc.general_binning.discard((200, R))
+    for call in range(2):
+        hp = nr.RasterizeHyperparam(image_size=R, anti_aliasing=False, draw_rgb=False, draw_depth=False)
+        maps = nr.rasterize_maps(v, idx, nr.RasterizeParam(), hp)
+        assert np.array_equal(maps["face_index_map"].cpu().numpy(), want), "call %d" % call
+        torch.cuda.synchronize()
+        sc.poll(block=True)
+        assert (200, R) in sc.general_binning
 
 
 def test_deterministic_mode_is_bit_reproducible(nr):
