@@ -56,6 +56,10 @@ enum {
 #define NR_DRAW_BACKSIDE 8    /* rasterize_param.py:20 */
 #define NR_ANTI_ALIASING 16   /* rasterize.py:227-228, 321-328 */
 #define NR_DETERMINISTIC 32   /* backward: fixed-order reduction instead of float atomics */
+#define NR_SPARSE_MAPS 128    /* forward: face_index_map / images_internal are only written where
+                                 nr_rasterize_backward reads them (non-empty 16x16 tiles; for images_internal
+                                 also the empty tiles next to one).  `images` is always complete.  Needs the forward's
+                                 tile_list passed on to the backward. */
 #define NR_GENERAL_BINNING 64 /* forward: never take the one-kernel small-mesh binning path (see nrBinStats) */
 
 /* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */
@@ -187,7 +191,8 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   zero_fill           optional, see nrZeroFill
  *
  * Every element of face_index_map / images / images_internal is written (empty tiles and background
- * pixels by the raster kernel itself): the caller does not initialise them.
+ * pixels by the raster kernel itself): the caller does not initialise them.  With NR_SPARSE_MAPS the two
+ * maps that only the backward consumes are left untouched where it never looks.
  */
 NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,

@@ -24,6 +24,7 @@ NR_DRAW_BACKSIDE = 8
 NR_ANTI_ALIASING = 16
 NR_DETERMINISTIC = 32
 NR_GENERAL_BINNING = 64
+NR_SPARSE_MAPS = 128
 
 # every symbol include/nr_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (

@@ -231,6 +231,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     }
     if (lights && rgb) ra.lights.backgrounds = lights->backgrounds;
 
+    ra.sparse_maps = (cfg->flags & NR_SPARSE_MAPS) ? 1 : 0;
     ra.num_zero = 0;
     if (zero_fill) {
         if (zero_fill->count < 0 || zero_fill->count > 4) return fail(NR_ERR_INVALID_ARGUMENT, "zero_fill: count outside 0..4");

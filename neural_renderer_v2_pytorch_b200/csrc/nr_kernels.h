@@ -58,6 +58,7 @@ struct RasterArgs {
     const int32_t *faces;   // [nf, 3] vertex ids (null: 3f..3f+2), only read when lights are on
     int nv;
     LightArgs lights;
+    int sparse_maps;        // fim / internal only where the backward reads them (see NR_SPARSE_MAPS)
     // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
     int num_zero;
     void *zero_ptr[4];

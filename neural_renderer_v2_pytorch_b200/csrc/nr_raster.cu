@@ -95,26 +95,47 @@ __device__ __forceinline__ float background_value(const RasterArgs &a, int b, in
     return __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * a.R + u) * a.R + v);
 }
 
-__device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane) {
+// `sparse`: write only what nr_rasterize_backward reads, i.e. not the face index of an empty tile, and
+// its internal-resolution image (anti-aliasing) only when a neighbouring tile is non-empty (the stencil
+// of a foreground pixel reaches one pixel into the next tile).
+__device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane, bool sparse) {
     const int R = a.R, S = a.S, C = a.C;
     const bool aa = (a.flags & FLAG_AA) != 0;
+    bool need_fim = true, need_internal = true;
+    if (sparse) {
+        need_fim = false;
+        if (aa) {
+            const int *tc = a.tile_count + (size_t)b * a.ntx * a.ntx;
+            int any = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int x = tx + dx, y = ty + dy;
+                    if (x >= 0 && y >= 0 && x < a.ntx && y < a.ntx) any |= __ldg(tc + y * a.ntx + x);
+                }
+            need_internal = any != 0;
+        }
+    }
     if ((R & 15) == 0 && !a.lights.backgrounds) {
         // vector path: a tile row is 64 aligned bytes in every plane; the flipped tile is again a tile
         const int r = lane >> 2, q = (lane & 3) * 4;
         const int4 m1 = make_int4(-1, -1, -1, -1);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (need_fim) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int y = ty * TILE + r + 8 * h;
-            *reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q) = m1;
+            for (int h = 0; h < 2; ++h) {
+                const int y = ty * TILE + r + 8 * h;
+                *reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q) = m1;
+            }
         }
         if (!a.images) return;
         const int u0 = R - TILE - ty * TILE, v0 = R - TILE - tx * TILE;
         float *full = aa ? a.internal : a.images;          // internal-resolution planes
-        for (int c = 0; c < C; ++c) {
+        if (!aa || need_internal) {
+            for (int c = 0; c < C; ++c) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-                *reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q) = z;
+                for (int h = 0; h < 2; ++h)
+                    *reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q) = z;
+            }
         }
         if (aa) {
             for (int i = lane; i < C * 16; i += 32) {
@@ -127,12 +148,12 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
     for (int p = lane; p < TILE * TILE; p += 32) {
         const int xi = tx * TILE + (p & 15), yi = ty * TILE + (p >> 4);
         if (xi >= R || yi >= R) continue;
-        a.fim[((size_t)b * R + yi) * R + xi] = -1;
+        if (need_fim) a.fim[((size_t)b * R + yi) * R + xi] = -1;
         if (!a.images) continue;
         const int u = R - 1 - yi, v = R - 1 - xi;
         float *full = aa ? a.internal : a.images;
         for (int c = 0; c < C; ++c) {
-            full[(((size_t)b * C + c) * R + u) * R + v] = background_value(a, b, c, u, v);
+            if (!aa || need_internal) full[(((size_t)b * C + c) * R + u) * R + v] = background_value(a, b, c, u, v);
             if (aa && !(u & 1) && !(v & 1)) {
                 // rasterize.py:323-328 on a pure-background quad
                 const float sum = __fadd_rn(__fadd_rn(__fadd_rn(background_value(a, b, c, u, v), background_value(a, b, c, u + 1, v)),
@@ -166,6 +187,7 @@ k_raster(const RasterArgs a) {
     const TileList tl = open_tile_list(a.tile_list, a.B * a.ntx * a.ntx);
     const int items = tl.total * RASTER_WARPS;
     const bool aa = (a.flags & FLAG_AA) != 0;
+    const bool has_bg = a.lights.backgrounds != nullptr && (a.flags & FLAG_RGB);
     const bool pow2 = (R & (R - 1)) == 0;
     const float invR = 1.f / (float)R;          // exact for power-of-two R
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -173,7 +195,8 @@ k_raster(const RasterArgs a) {
     uint2 *my_bb = s_bb[wid];
 
     // ---- fill items (stores only), interleaved with the raster items: claim i also performs fill item i,
-    // so the fills drain to HBM all along the kernel instead of in one burst that would stall every warp.
+    // so the fills drain to HBM all along the kernel instead of in one burst that would stall every warp
+    // (a static share per warp was slower: the warps holding the heavy tiles kept their fills for the end).
     // Fill item i < B * tiles: tile i if it is empty; then 4 KB chunks of the caller's zero buffers.
     constexpr int ZCHUNK = 256;                 // int4 per chunk
     const int nt = a.ntx * a.ntx, all_tiles = a.B * nt;
@@ -185,8 +208,19 @@ k_raster(const RasterArgs a) {
     auto do_fill = [&](int i) {
         if (i < all_tiles) {
             if (__ldg(a.tile_count + i) != 0) return;
-            const int b = i / nt, tt = i - b * nt, ty = tt / a.ntx;
-            fill_empty_tile(a, b, tt - ty * a.ntx, ty, lane);
+            int b, tx, ty;
+            if ((a.ntx & (a.ntx - 1)) == 0) {       // power-of-two tile grid: shifts instead of divisions
+                const int sh = __ffs(a.ntx) - 1;
+                b = i >> (2 * sh);
+                ty = (i >> sh) & (a.ntx - 1);
+                tx = i & (a.ntx - 1);
+            } else {
+                b = i / nt;
+                const int tt = i - b * nt;
+                ty = tt / a.ntx;
+                tx = tt - ty * a.ntx;
+            }
+            fill_empty_tile(a, b, tx, ty, lane, a.sparse_maps != 0);
             return;
         }
         int j = i - all_tiles;
@@ -328,6 +362,20 @@ k_raster(const RasterArgs a) {
             __syncwarp();
         }
         // ---------------------------------------------- epilogue: every pixel of the block is written
+        if (__ballot_sync(0xffffffffu, best >= 0) == 0u && !has_bg) {
+            // nothing but (black) background in this block
+            if (valid) {
+                a.fim[((size_t)b * R + yi) * R + xi] = -1;
+                if (a.images) {
+                    const int u_ = R - 1 - yi, v_ = R - 1 - xi, C = a.C;
+                    float *full = aa ? a.internal : a.images;
+                    for (int c = 0; c < C; ++c) full[(((size_t)b * C + c) * R + u_) * R + v_] = 0.f;
+                    if (aa && !(xi & 1) && !(yi & 1))
+                        for (int c = 0; c < C; ++c) a.images[(((size_t)b * C + c) * a.S + (u_ >> 1)) * a.S + (v_ >> 1)] = 0.f;
+                }
+            }
+            continue;
+        }
         const bool fg = valid && best >= 0;
         float q[3] = {0.f, 0.f, 0.f};
         if (fg) {
@@ -352,7 +400,7 @@ k_raster(const RasterArgs a) {
             // one channel value of this pixel -> images (and the internal-resolution copy under AA)
             auto put = [&](int c, float val) {
                 // background pixels show the background picture (black without one)
-                if (!fg && valid) val = background_value(a, b, c, u_, v_);
+                if (has_bg && !fg && valid) val = background_value(a, b, c, u_, v_);
                 if (!aa) {
                     if (valid) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
                     return;

@@ -151,7 +151,7 @@ def _zero_fill_struct(buffers):
     return ctypes.byref(z)
 
 
-def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None, zero=()):
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None, zero=(), sparse=False):
     """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
     Returns (images, internal, fim, wmap, dmap, tile_list)."""
     L = _lib.lib()
@@ -192,6 +192,8 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         track = not sc.pending and not capturing
         if (cfg.num_faces, R) in sc.general_binning or FORCE_GENERAL_BINNING:
             cfg.flags |= _lib.NR_GENERAL_BINNING
+        if sparse and not want_maps:
+            cfg.flags |= _lib.NR_SPARSE_MAPS     # fim / internal image are only handed to the backward
         if track:
             sc.last_shape = (cfg.num_faces, R)
         rc = L.nr_rasterize_forward(
@@ -250,7 +252,8 @@ class _Rasterize(torch.autograd.Function):
             if gv is not None or gvt is not None or gtex is not None:
                 ctx.grad_bufs = (gv, gvt, gtex)
         images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg,
-                                                               ctx.grad_bufs or ())
+                                                               ctx.grad_bufs or (),
+                                                               sparse=not (bg is not None and need[4]))
         ctx.cfg = cfg
         ctx.bg_dtype = backgrounds.dtype if backgrounds is not None else None
         ctx.has_tex = tex is not None
