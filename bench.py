@@ -235,10 +235,13 @@ def run_ours(args):
             target = fn(nr.perspective(nr.look_at(tv.to(dev)[None].expand(B, -1, -1), eye_d)), faces,
                         nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
         params = [param]
+        rend = nr.Renderer()
+        rend.image_size, rend.anti_aliasing, rend.viewpoints = S, w["aa"], eye_d
 
         def step_fn():
-            vs = nr.perspective(nr.look_at(nr.parallel.share_across_views(param, B), eye_d))
-            images = fn(vs, faces, nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
+            # Renderer.render_silhouettes: fused camera transform + rasterizer; the backward sums the
+            # gradient over the local views and all-reduces it over the ranks (parallel.py)
+            images = rend.render_silhouettes(nr.parallel.share_across_views(param, B), faces)
             ((images - target) ** 2).sum().backward()
             return images
     elif w.get("renderer"):
@@ -270,11 +273,20 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         eager_step()
     barrier()
-    # the whole step (forward + backward, ~12 short launches) is captured once in a CUDA graph and
-    # replayed: every replay does the full work on the device; --eager launches from Python instead
-    # (also used when the step contains an NCCL all-reduce)
-    use_graph = not args.eager and not (shared and world > 1)
-    run_step = nr.capture_step(step_fn, params=params, warmup=2) if use_graph else eager_step
+    # the whole step (forward + backward, a handful of launches, and for a shared mesh the NCCL
+    # all-reduce of its gradient) is captured once in a CUDA graph and replayed: every replay does the
+    # full work on the device; --eager launches from Python instead
+    use_graph = not args.eager
+    run_step = eager_step
+    if use_graph:
+        try:
+            run_step = nr.capture_step(step_fn, params=params, warmup=2)
+        except Exception as e:      # e.g. a collective that cannot be captured on this NCCL build
+            if not (shared and world > 1):
+                raise
+            sys.stderr.write("bench.py: graph capture with the all-reduce failed (%s); launching eagerly\n" % e)
+            use_graph = False
+            torch.cuda.synchronize(dev)
     for _ in range(max(args.warmup, 3)):      # warm replays: clocks ramp up, lazy kernel loading is over
         run_step()
     barrier()
@@ -368,9 +380,18 @@ def run_ours(args):
     h2d = sum(h_.numel() * 4 for h_ in hosts)
     d2h = gv_host.numel() * 4 + 4
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroy_process_group() can block for minutes on a communicator
+        whose all-reduce lives in a captured CUDA graph, and nothing is left to clean up anyway."""
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline of the dominant kernel
@@ -421,8 +442,7 @@ def run_ours(args):
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 # ------------------------------------------------------------------------------------- CPU side

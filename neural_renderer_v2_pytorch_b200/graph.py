@@ -16,6 +16,7 @@ land in one graph) and returns a callable that replays it with ~10 us of host wo
 The reference has nothing comparable (every call synchronises with the host several times per view,
 utils.py:111-112)."""
 import torch
+import torch.distributed
 
 
 def capture_step(step, params=(), warmup=3):
@@ -38,8 +39,13 @@ def capture_step(step, params=(), warmup=3):
     for p in params:
         p.grad = None
     graph = torch.cuda.CUDAGraph()
-    # capture on the stream the warm-up ran on: the rasterizer keeps one workspace per stream
-    with torch.cuda.graph(graph, stream=side):
+    # capture on the stream the warm-up ran on: the rasterizer keeps one workspace per stream.
+    # With a process group alive its watchdog thread polls CUDA events; "thread_local" keeps those calls
+    # legal while this thread captures (a step may contain the all-reduce of parallel.share_across_views).
+    mode = "global"
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        mode = "thread_local"
+    with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
         out = step()
 
     def replay():
