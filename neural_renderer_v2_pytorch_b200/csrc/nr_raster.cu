@@ -90,17 +90,19 @@ __device__ __forceinline__ bool block_outside_face(float x0, float y0, float x1,
 // coming backward).  Pixels of non-empty tiles are all written by the raster items, foreground or not.
 
 // value of rgb channel c behind a background pixel at OUTPUT position (u, v) of view b
+template <bool FULL>
 __device__ __forceinline__ float background_value(const RasterArgs &a, int b, int c, int u, int v) {
-    if (!a.lights.backgrounds || c >= 3 || !(a.flags & FLAG_RGB)) return 0.f;
+    if (!FULL || !a.lights.backgrounds || c >= 3 || !(a.flags & FLAG_RGB)) return 0.f;
     return __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * a.R + u) * a.R + v);
 }
 
 // `sparse`: write only what nr_rasterize_backward reads, i.e. not the face index of an empty tile, and
 // its internal-resolution image (anti-aliasing) only when a neighbouring tile is non-empty (the stencil
 // of a foreground pixel reaches one pixel into the next tile).
+template <bool AA, bool FULL>
 __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane, bool sparse) {
     const int R = a.R, S = a.S, C = a.C;
-    const bool aa = (a.flags & FLAG_AA) != 0;
+    constexpr bool aa = AA;
     bool need_fim = true, need_internal = true;
     if (sparse) {
         need_fim = false;
@@ -115,7 +117,7 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
             need_internal = any != 0;
         }
     }
-    if ((R & 15) == 0 && !a.lights.backgrounds) {
+    if (!FULL || ((R & 15) == 0 && !a.lights.backgrounds)) {
         // vector path: a tile row is 64 aligned bytes in every plane; the flipped tile is again a tile
         const int r = lane >> 2, q = (lane & 3) * 4;
         const int4 m1 = make_int4(-1, -1, -1, -1);
@@ -124,7 +126,7 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int y = ty * TILE + r + 8 * h;
-                *reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q) = m1;
+                __stcs(reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q), m1);
             }
         }
         if (!a.images) return;
@@ -134,17 +136,19 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
             for (int c = 0; c < C; ++c) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    *reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q) = z;
+                    __stcs(reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q), z);
             }
         }
         if (aa) {
             for (int i = lane; i < C * 16; i += 32) {
                 const int c = i >> 4, rr = (i >> 1) & 7, hh = (i & 1) * 4;
-                *reinterpret_cast<float4 *>(a.images + (((size_t)b * C + c) * S + (u0 >> 1) + rr) * S + (v0 >> 1) + hh) = z;
+                __stcs(reinterpret_cast<float4 *>(a.images + (((size_t)b * C + c) * S + (u0 >> 1) + rr) * S + (v0 >> 1) + hh), z);
             }
         }
         return;
     }
+    // (the launcher sends everything the vector path cannot do to the FULL variant)
+    if constexpr (FULL) {
     for (int p = lane; p < TILE * TILE; p += 32) {
         const int xi = tx * TILE + (p & 15), yi = ty * TILE + (p >> 4);
         if (xi >= R || yi >= R) continue;
@@ -153,15 +157,16 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
         const int u = R - 1 - yi, v = R - 1 - xi;
         float *full = aa ? a.internal : a.images;
         for (int c = 0; c < C; ++c) {
-            if (!aa || need_internal) full[(((size_t)b * C + c) * R + u) * R + v] = background_value(a, b, c, u, v);
+            if (!aa || need_internal) full[(((size_t)b * C + c) * R + u) * R + v] = background_value<FULL>(a, b, c, u, v);
             if (aa && !(u & 1) && !(v & 1)) {
                 // rasterize.py:323-328 on a pure-background quad
-                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(background_value(a, b, c, u, v), background_value(a, b, c, u + 1, v)),
-                                                      background_value(a, b, c, u, v + 1)), background_value(a, b, c, u + 1, v + 1));
+                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(background_value<FULL>(a, b, c, u, v), background_value<FULL>(a, b, c, u + 1, v)),
+                                                      background_value<FULL>(a, b, c, u, v + 1)), background_value<FULL>(a, b, c, u + 1, v + 1));
                 a.images[(((size_t)b * C + c) * S + (u >> 1)) * S + (v >> 1)] = __fmul_rn(sum, 0.25f);
             }
         }
     }
+}
 }
 
 // Persistent kernel over the non-empty tiles.  The unit of work is one WARP = one 8x4 pixel block
@@ -173,6 +178,11 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
 // Background pixels were pre-filled by launch_raster, so only foreground pixels are written.
 constexpr int RASTER_WARPS = TILE_THREADS / 32;
 
+// Variants: RGB (texture sampling), AA (2x2 mean epilogue), FULL (everything optional: lights,
+// backgrounds, the weight / depth maps of rasterize_maps, resolutions that are no multiple of 16).
+// The plain variants leave that code out, which halves their size: at 75 KB the one-size kernel spent
+// as many issue slots waiting for instructions as for memory.
+template <bool RGB, bool AA, bool FULL>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_raster(const RasterArgs a) {
     __shared__ float4 s_rec[RASTER_WARPS][32][4];
@@ -186,8 +196,8 @@ k_raster(const RasterArgs a) {
     const int R = a.R;
     const TileList tl = open_tile_list(a.tile_list, a.B * a.ntx * a.ntx);
     const int items = tl.total * RASTER_WARPS;
-    const bool aa = (a.flags & FLAG_AA) != 0;
-    const bool has_bg = a.lights.backgrounds != nullptr && (a.flags & FLAG_RGB);
+    constexpr bool aa = AA;
+    const bool has_bg = FULL && RGB && a.lights.backgrounds != nullptr;
     const bool pow2 = (R & (R - 1)) == 0;
     const float invR = 1.f / (float)R;          // exact for power-of-two R
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -220,7 +230,7 @@ k_raster(const RasterArgs a) {
                 ty = tt / a.ntx;
                 tx = tt - ty * a.ntx;
             }
-            fill_empty_tile(a, b, tx, ty, lane, a.sparse_maps != 0);
+            fill_empty_tile<AA, FULL>(a, b, tx, ty, lane, a.sparse_maps != 0);
             return;
         }
         int j = i - all_tiles;
@@ -234,7 +244,7 @@ k_raster(const RasterArgs a) {
 #pragma unroll
             for (int s = 0; s < ZCHUNK / 32; ++s) {
                 const size_t idx = base + lane + 32 * s;
-                if (idx < n16) dst[idx] = make_int4(0, 0, 0, 0);
+                if (idx < n16) __stcs(dst + idx, make_int4(0, 0, 0, 0));
             }
             if (j == zero_chunks[k] - 1 && lane < (int)((a.zero_bytes[k] & 15) >> 2))
                 reinterpret_cast<int32_t *>(dst + n16)[lane] = 0;
@@ -366,7 +376,7 @@ k_raster(const RasterArgs a) {
             // nothing but (black) background in this block
             if (valid) {
                 a.fim[((size_t)b * R + yi) * R + xi] = -1;
-                if (a.images) {
+                if (!FULL || a.images) {
                     const int u_ = R - 1 - yi, v_ = R - 1 - xi, C = a.C;
                     float *full = aa ? a.internal : a.images;
                     for (int c = 0; c < C; ++c) full[(((size_t)b * C + c) * R + u_) * R + v_] = 0.f;
@@ -386,21 +396,21 @@ k_raster(const RasterArgs a) {
         float dm = 0.f;
         if (valid) a.fim[pix] = fg ? best : -1;
         if (fg) {
-            if (a.wmap) {
+            if (FULL && a.wmap) {
                 float *w = a.wmap + pix * 3;
                 w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
             }
-            if ((a.flags & FLAG_DEPTH) || a.dmap)
+            if ((a.flags & FLAG_DEPTH) || (FULL && a.dmap))
                 dm = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fdiv_rn(q[0], bz0), __fdiv_rn(q[1], bz1)), __fdiv_rn(q[2], bz2)));
-            if (a.dmap) a.dmap[pix] = dm;
+            if (FULL && a.dmap) a.dmap[pix] = dm;
         }
-        if (a.images) {
+        if (!FULL || a.images) {
             const int C = a.C, S = a.S;
             const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
             // one channel value of this pixel -> images (and the internal-resolution copy under AA)
             auto put = [&](int c, float val) {
                 // background pixels show the background picture (black without one)
-                if (has_bg && !fg && valid) val = background_value(a, b, c, u_, v_);
+                if (has_bg && !fg && valid) val = background_value<FULL>(a, b, c, u_, v_);
                 if (!aa) {
                     if (valid) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
                     return;
@@ -418,7 +428,7 @@ k_raster(const RasterArgs a) {
                 }
             };
             int c = 0;
-            if (a.flags & FLAG_RGB) {
+            if (RGB) {
                 float rgb[3] = {0.f, 0.f, 0.f};
                 if (fg) {
                     const int32_t *fti = a.ft + 3 * (size_t)best;
@@ -433,7 +443,7 @@ k_raster(const RasterArgs a) {
                     }
                     const float z[3] = {bz0, bz1, bz2};
                     sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
-                    if (a.lights.num > 0) {
+                    if (FULL && a.lights.num > 0) {
                         // smooth normal map (rasterize.py:186-187) and light accumulation (:252-283)
                         float n[3] = {0.f, 0.f, 0.f}, cw[3];
                         const float *vnb = a.lights.vnormals + (size_t)b * a.nv * 3;
@@ -497,8 +507,21 @@ cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     const long long tiles = (long long)a.ntx * a.ntx * a.B;
     const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
+    const bool rgb = (a.flags & FLAG_RGB) != 0, aa = (a.flags & FLAG_AA) != 0;
+    // everything optional goes to the FULL variants
+    const bool full = a.lights.num > 0 || a.lights.backgrounds || a.wmap || a.dmap || !a.images || (a.R & 15);
     ProfScope p(PROF_RASTER, stream);
-    k_raster<<<grid, TILE_THREADS, 0, stream>>>(a);
+    const int variant = (rgb ? 1 : 0) | (aa ? 2 : 0) | (full ? 4 : 0);
+    switch (variant) {
+        case 0: k_raster<false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 1: k_raster<true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 2: k_raster<false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 3: k_raster<true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 4: k_raster<false, false, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 5: k_raster<true, false, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 6: k_raster<false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        default: k_raster<true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+    }
     return cudaGetLastError();
 }
 
