@@ -279,7 +279,9 @@ k_backward(const BackwardArgs a) {
     int tap[4] = {-1, -1, -1, -1};
     int cell = 0;
     bool has_tex = false;
-    const bool rgb = (a.flags & FLAG_RGB) != 0;
+    // CT = 1 is a lone silhouette or depth channel, CT >= 3 always holds the three colour channels
+    const bool rgb = (CT == 1) ? false : ((CT >= 3) ? true : (a.flags & FLAG_RGB) != 0);
+    constexpr bool LIT = (CT == 0);      // lights only in the generic variants (keeps the common ones small)
     if (fg) {
         if (a.faces) {
             vid[0] = __ldg(a.faces + 3 * (size_t)f);
@@ -318,7 +320,7 @@ k_backward(const BackwardArgs a) {
                 }
                 float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f}, tw[4], g[3], rgb_tex[3];
                 float cw[3] = {1.f, 1.f, 1.f}, nrm[3] = {0.f, 0.f, 0.f};
-                const bool lit = a.lights.num > 0;
+                const bool lit = LIT && a.lights.num > 0;
                 if (lit) {
                     const float *vnb = a.lights.vnormals + (size_t)b * a.nv * 3;
 #pragma unroll
@@ -454,7 +456,7 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     } else if (a.grad_vt) {
         k_backward<0, true, false><<<grid, block, 0, stream>>>(a);
     } else {
-        switch (a.C) {
+        switch (a.lights.num > 0 ? 0 : a.C) {
             case 1: k_backward<1, false, false><<<grid, block, 0, stream>>>(a); break;
             case 3: k_backward<3, false, false><<<grid, block, 0, stream>>>(a); break;
             case 4: k_backward<4, false, false><<<grid, block, 0, stream>>>(a); break;
