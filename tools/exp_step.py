@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Developer timing loop: ms per captured fwd+bwd step of one bench workload, for each value of the
 NR_EXP environment variable given on the command line (experiment switches compiled into the library
-while a change is being evaluated; none are active in a committed build).
+while a change is being evaluated; none are active in a committed build), or for an alternative build
+of the library: `altX` loads csrc/libnr_b200_altX.so.  Boxes differ by ~2 %, so A and B go in one call.
 
-    python tools/exp_step.py cfg2 0 1 2
+    python tools/exp_step.py cfg2 0 1 2 alt
 """
 import os
 import subprocess
@@ -17,6 +18,9 @@ def child(workload):
     import torch
     import bench
     import neural_renderer_v2_pytorch_b200 as nr
+    if os.environ.get("NR_LIB_ALT"):        # A/B against an alternative build: csrc/libnr_b200_<name>.so
+        from neural_renderer_v2_pytorch_b200 import _lib
+        _lib.LIB_PATH = os.path.join(_lib.CSRC, "libnr_b200_%s.so" % os.environ["NR_LIB_ALT"])
     w = bench.WORKLOADS[workload]
     dev = torch.device("cuda:0")
     inp = bench.make_inputs(w, 1000, dev, nr)
@@ -54,7 +58,7 @@ def child(workload):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 200)
-    print("NR_EXP=%s %s: %.4f ms/step  (grad checksum %.6g)" % (os.environ.get("NR_EXP", "0"), workload, best,
+    print("NR_EXP=%s %s: %.4f ms/step  (grad checksum %.6g)" % (os.environ.get("NR_LIB_ALT", "") + os.environ.get("NR_EXP", "0"), workload, best,
                                                             float(v.grad.double().abs().sum())))
 
 
@@ -65,4 +69,6 @@ if __name__ == "__main__":
         wl = sys.argv[1]
         for x in sys.argv[2:] or ["0"]:
             env = dict(os.environ, NR_EXP=x, NR_EXP_CHILD="1")
+            if x.startswith("alt"):
+                env.update(NR_EXP="0", NR_LIB_ALT=x)
             subprocess.run([sys.executable, os.path.abspath(__file__), wl], env=env)
