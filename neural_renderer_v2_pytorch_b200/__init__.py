@@ -10,6 +10,8 @@ from .lights import Light, DirectionalLight, AmbientLight, SpecularLight
 from .load_obj import load_obj
 from .look import look
 from .look_at import look_at
+from .mesh import Mesh
+from .optimizers import Adam
 from .perspective import perspective
 from .rasterize_param import RasterizeParam, RasterizeHyperparam
 from .rasterize import (rasterize_silhouettes, rasterize_rgba, rasterize_rgb, rasterize_depth,

@@ -473,6 +473,46 @@ def test_fused_matches_oracle_pipeline_midsize(nr):
     grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
 
 
+def test_forward_zero_fills_the_gradient_accumulators(nr):
+    """nrZeroFill: buffers handed to the forward come back zero (whatever their size modulo 16 bytes),
+    every output element is written, and gradients of odd-sized textures still match the oracle."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    B, S = 2, 40
+    g = torch.Generator().manual_seed(9)
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20, torch.rand(B, generator=g) * 360)
+    vs = nr.perspective(nr.look_at(vw, eye)).cuda()
+    faces = torch.from_numpy(d["faces"]).cuda()
+    hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=True, draw_rgb=False, draw_depth=False)
+    cfg, faces_d, *_ = rz._prepare(vs, faces, nr.RasterizeParam(), hp)
+    bufs = [torch.full((n,), float("nan"), device="cuda") for n in (1, 3, 4, 1021, 4096 * 3 + 2)]
+    for group in (bufs[:4], bufs[4:]):
+        images, internal, fim, _, _, _ = rz._forward_call(cfg, vs.contiguous(), faces_d, None, None, None, False, zero=group)
+        for t in group:
+            assert float(t.abs().sum()) == 0.0 and not torch.isnan(t).any()
+        assert not torch.isnan(images).any() and not torch.isnan(internal).any()
+        assert int(fim.min()) >= -1 and int(fim.max()) < faces.shape[0]
+    # textures whose byte size is not a multiple of 16
+    ts_faces = faces.shape[0]
+    vt_np, ft_np, tex_np = nr.create_textures(ts_faces, 1)
+    H, W = tex_np.shape[1] + 1, tex_np.shape[2] + 3          # 2 * 3 * 51 * 53 * 4 bytes = 8 (mod 16)
+    tex0 = torch.rand((B, 3, H, W), generator=g)
+    assert (tex0.numel() * 4) % 16 != 0
+    vt0 = torch.from_numpy(vt_np)[None].repeat(B, 1, 1)
+    G = torch.randn((B, 4, S, S), generator=g)
+    v0 = vs.cpu().clone().requires_grad_(True)
+    t0 = tex0.clone().requires_grad_(True)
+    (ref.rasterize(v0, faces.cpu(), S, True, draw_rgb=True, draw_silhouettes=True, vertices_textures=vt0,
+                   faces_textures=ft_np, textures=t0) * G).sum().backward()
+    v1 = vs.clone().requires_grad_(True)
+    t1 = tex0.clone().cuda().requires_grad_(True)
+    p = nr.RasterizeParam(vertices_textures=vt0.cuda(), faces_textures=torch.from_numpy(ft_np).cuda(), textures=t1)
+    (nr.rasterize_rgba(v1, faces, p, nr.RasterizeHyperparam(image_size=S, anti_aliasing=True)) * G.cuda()).sum().backward()
+    grad_close(v1.grad.cpu().numpy(), v0.grad.numpy(), "grad_vertices")
+    grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
+
+
 @pytest.mark.parametrize("aa,mode", [(False, "picture"), (True, "picture"), (True, "color")])
 def test_backgrounds(nr, aa, mode):
     """Backgrounds.  The reference's blend_backgrounds fails on torch tensors

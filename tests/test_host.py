@@ -195,3 +195,23 @@ def test_bench_bytes_formula():
     assert abs((fwd + bwd) / 1e6 - 18.28) < 0.01
     fwd, bwd = bench.algorithmic_bytes(nv=1292, nf=2464, T=0, P=512 * 512, C=1, S=512)
     assert abs((fwd + bwd) / 1e6 - 10.55) < 0.03
+
+
+def test_mesh_and_adam_exist_and_work(tmp_path):
+    """Names of the reference package outside the accelerated path (mesh.py, optimizers.py)."""
+    obj = tmp_path / "tri.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nf 1 2 3\nf 1 3 4\n")
+    m = nr.Mesh(str(obj), texture_size=2)
+    v, f, t = m.get_batch(3)
+    assert v.shape == (3, 4, 3) and f.shape == (3, 2, 3) and t.shape == (3, 2, 2, 2, 2, 3)
+    assert float(t.min()) > 0 and float(t.max()) < 1
+    # Adam: chainer's bias-corrected update with the per-parameter factor param.lr
+    p = torch.nn.Parameter(torch.tensor([1.0, -2.0]))
+    q = torch.nn.Parameter(torch.tensor([3.0]))
+    q.lr = 0.0
+    opt = nr.Adam([p, q], alpha=0.1)
+    (p.pow(2).sum() + q.sum()).backward()
+    opt.step()
+    # first step of Adam moves every coordinate by alpha against the sign of its gradient
+    assert torch.allclose(p.detach(), torch.tensor([0.9, -1.9]), atol=1e-6)
+    assert float(q) == 3.0
