@@ -473,12 +473,14 @@ def test_fused_matches_oracle_pipeline_midsize(nr):
     grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
 
 
-def test_forward_zero_fills_the_gradient_accumulators(nr):
+@pytest.mark.parametrize("S", [40, 36])
+def test_forward_zero_fills_the_gradient_accumulators(nr, S):
     """nrZeroFill: buffers handed to the forward come back zero (whatever their size modulo 16 bytes),
-    every output element is written, and gradients of odd-sized textures still match the oracle."""
+    every output element is written, and gradients of odd-sized textures still match the oracle.
+    S = 36 (internal resolution 72, no multiple of the tile size) takes the scalar fill path."""
     from neural_renderer_v2_pytorch_b200 import rasterize as rz
     d = np.load(os.path.join(GOLDEN, "teapot.npz"))
-    B, S = 2, 40
+    B = 2
     g = torch.Generator().manual_seed(9)
     vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
     eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20, torch.rand(B, generator=g) * 360)
