@@ -60,6 +60,10 @@ enum {
                                  nr_rasterize_backward reads them (non-empty 16x16 tiles; for images_internal
                                  also the empty tiles next to one).  `images` is always complete.  Needs the forward's
                                  tile_list passed on to the backward. */
+#define NR_FINE_TILES 256     /* forward: bin into 8x8 instead of 16x16 tiles (general binning path).  For dense
+                                 meshes (nrBinStats.max_tile_faces in the hundreds): lists four times shorter.
+                                 tile_list is then in 8x8 units, [8 + 16 * B * ceil(R/8)^2] ints, and must NOT
+                                 be passed to nr_rasterize_backward (pass NULL); NR_SPARSE_MAPS is ignored. */
 #define NR_GENERAL_BINNING 64 /* forward: never take the one-kernel small-mesh binning path (see nrBinStats) */
 
 /* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */

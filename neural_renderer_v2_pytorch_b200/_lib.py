@@ -25,6 +25,7 @@ NR_ANTI_ALIASING = 16
 NR_DETERMINISTIC = 32
 NR_GENERAL_BINNING = 64
 NR_SPARSE_MAPS = 128
+NR_FINE_TILES = 256
 
 # every symbol include/nr_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (

@@ -33,8 +33,8 @@ struct Carve {
 };
 
 // header and tile_count must be adjacent (one memset clears both)
-Carve carve(void *base, int B, int nf, int R, long long pair_capacity) {
-    const int ntx = (R + nr::TILE - 1) / nr::TILE;
+Carve carve(void *base, int B, int nf, int R, long long pair_capacity, int tile) {
+    const int ntx = (R + tile - 1) / tile;
     const size_t nt = (size_t)B * ntx * ntx;
     char *p = (char *)base;
     size_t off = 0;
@@ -69,6 +69,9 @@ int sm_count_cached() {
     }
     return cached[dev];
 }
+
+// tile edge of the binning: 16, or 8 with NR_FINE_TILES (which implies the general binning path)
+int tile_edge(const nrRasterConfig *cfg) { return (cfg->flags & NR_FINE_TILES) ? nr::FINE_TILE : nr::TILE; }
 
 int check_config(const nrRasterConfig *cfg) {
     if (!cfg) return fail(NR_ERR_INVALID_ARGUMENT, "config is NULL");
@@ -143,7 +146,7 @@ size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg) {
 size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
     if (!cfg) return 0;
     const int R = cfg->image_size * ((cfg->flags & NR_ANTI_ALIASING) ? 2 : 1);
-    return carve(nullptr, cfg->batch, cfg->num_faces, R, pair_capacity).bytes;
+    return carve(nullptr, cfg->batch, cfg->num_faces, R, pair_capacity, tile_edge(cfg)).bytes;
 }
 
 int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
@@ -167,7 +170,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
         return fail(NR_ERR_INVALID_ARGUMENT, "anti-aliasing needs images_internal");
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(NR_ERR_INVALID_ARGUMENT, "workspace NULL or not 256-byte aligned");
     if (pair_capacity < 0 || pair_capacity > 0x7fffffffLL) return fail(NR_ERR_INVALID_ARGUMENT, "pair_capacity out of range");
-    const Carve c = carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity);
+    const int tile = tile_edge(cfg);
+    const Carve c = carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity, tile);
     if (c.bytes > workspace_bytes) return fail(NR_ERR_WORKSPACE_TOO_SMALL, "workspace smaller than nr_workspace_bytes()");
     if (cfg->batch == 0) return NR_OK;
 
@@ -179,7 +183,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.nf = cfg->num_faces;
     ba.R = R;
     ba.draw_backside = (cfg->flags & NR_DRAW_BACKSIDE) ? 1 : 0;
-    ba.ntx = (R + nr::TILE - 1) / nr::TILE;
+    ba.ntx = (R + tile - 1) / tile;
+    ba.tile_shift = tile == nr::TILE ? 4 : 3;
     ba.rec = c.rec;
     ba.tile_count = c.tile_count;
     ba.tile_offset = c.tile_offset;
@@ -189,7 +194,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.hdr = c.hdr;
     ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
-    ba.one_cta_per_view = (cfg->flags & NR_GENERAL_BINNING) ? 0 : 1;
+    ba.one_cta_per_view = (cfg->flags & (NR_GENERAL_BINNING | NR_FINE_TILES)) ? 0 : 1;
 
     nr::RasterArgs ra;
     ra.rec = c.rec;
@@ -231,7 +236,9 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     }
     if (lights && rgb) ra.lights.backgrounds = lights->backgrounds;
 
-    ra.sparse_maps = (cfg->flags & NR_SPARSE_MAPS) ? 1 : 0;
+    ra.fine = tile != nr::TILE;
+    // with 8x8 tiles the backward walks every 16x16 tile itself, so the maps must be complete
+    ra.sparse_maps = ((cfg->flags & NR_SPARSE_MAPS) && !ra.fine) ? 1 : 0;
     ra.num_zero = 0;
     if (zero_fill) {
         if (zero_fill->count < 0 || zero_fill->count > 4) return fail(NR_ERR_INVALID_ARGUMENT, "zero_fill: count outside 0..4");

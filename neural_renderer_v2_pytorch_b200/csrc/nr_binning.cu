@@ -12,7 +12,7 @@
 //                   counts the face into every 16x16 tile its pixel box touches.
 //   k_scan_tiles  : exclusive prefix sum of the per-tile counts (one CTA per view).
 //   k_scatter     : writes face ids into the tile segments (slot order is arbitrary ...)
-//   k_sort_tiles  : ... so every list is sorted in place: <= 128 ids by one warp in registers,
+//   k_sort_tiles  : ... so every list is sorted in place: <= 256 ids by one warp in registers,
 //                   <= 8192 by a CTA in shared memory, longer ones by a CTA in global memory.
 #include <cooperative_groups.h>
 
@@ -85,7 +85,7 @@ __device__ __forceinline__ bool make_face_record(const float *__restrict__ vb, c
 __global__ void __launch_bounds__(256)
 k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces, int B, int nv,
               int nf, int R, int draw_backside, FaceRec *__restrict__ rec,
-              int *__restrict__ tile_count, int ntx, BinHeader *__restrict__ hdr) {
+              int *__restrict__ tile_count, int ntx, int tsh, BinHeader *__restrict__ hdr) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)B * nf) return;
     const int b = (int)(idx / nf), f = (int)(idx % nf);
@@ -96,7 +96,7 @@ k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces
     if (!alive) return;
 
     int *tc = tile_count + (size_t)b * ntx * ntx;
-    const int tx0 = xlo / TILE, tx1 = xhi / TILE, ty0 = ylo / TILE, ty1 = yhi / TILE;
+    const int tx0 = xlo >> tsh, tx1 = xhi >> tsh, ty0 = ylo >> tsh, ty1 = yhi >> tsh;
     for (int ty = ty0; ty <= ty1; ++ty)
         for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&tc[ty * ntx + tx], 1);
 }
@@ -186,7 +186,7 @@ k_scan_tiles(const int *__restrict__ tile_count, int *__restrict__ tile_offset,
 }
 
 __global__ void __launch_bounds__(256)
-k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restrict__ tile_cursor,
+k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int tsh, int *__restrict__ tile_cursor,
           int32_t *__restrict__ pairs, long long pair_capacity, const BinHeader *__restrict__ hdr) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)B * nf) return;
@@ -198,7 +198,7 @@ k_scatter(const FaceRec *__restrict__ rec, int B, int nf, int ntx, int *__restri
     const int ylo = by & 0xffff, yhi = by >> 16;
     const int b = (int)(idx / nf), f = (int)(idx % nf);
     int *cur = tile_cursor + (size_t)b * ntx * ntx;
-    const int tx0 = xlo / TILE, tx1 = xhi / TILE, ty0 = ylo / TILE, ty1 = yhi / TILE;
+    const int tx0 = xlo >> tsh, tx1 = xhi >> tsh, ty0 = ylo >> tsh, ty1 = yhi >> tsh;
     for (int ty = ty0; ty <= ty1; ++ty)
         for (int tx = tx0; tx <= tx1; ++tx) {
             const int slot = atomicAdd(&cur[ty * ntx + tx], 1);
@@ -461,10 +461,10 @@ k_bin_view(const float *__restrict__ verts, const int32_t *__restrict__ faces, i
 
 // Ascending in-place sort of every tile list of up to SMEM_SORT_CAP faces, grid-stride over the work
 // list.  Lists that the scatter kernel happened to fill in face order only pay the sortedness check.
-// Lists of <= 128 ids are rank-sorted in registers by one warp (four ids per lane); longer ones by
+// Lists of <= 256 ids are rank-sorted in registers by one warp (up to eight ids per lane); longer ones by
 // the whole CTA with a bitonic network in shared memory.
 constexpr int SORT_WARPS = 8;
-constexpr int SORT_PER_LANE = 4;
+constexpr int SORT_PER_LANE = 8;
 constexpr int SORT_WARP_MAX = 32 * SORT_PER_LANE;     // lists up to this length: one warp each
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict__ pairs,
@@ -477,42 +477,17 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
     const TileList tl = open_tile_list(tile_list, cap);
     const int count = tl.total;
 
-    // ---- pass A: lists of up to 128 ids, one warp per list, ids held in registers
-    // (position p of the list lives in register p / 32 of lane p % 32)
+    // ---- pass A: lists of up to 256 ids, one warp per list, rank sort with the ids in registers
+    // (warp_rank_sort reads the whole list before it writes, so sorting in place is safe)
     for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
         const int4 e = tile_entry(tl, w);
         const int n = e.w;
         if (n < 2 || n > SORT_WARP_MAX) continue;
         int32_t *a = pairs + e.z;
-        int v[SORT_PER_LANE];
-#pragma unroll
-        for (int k = 0; k < SORT_PER_LANE; ++k) v[k] = (k * 32 + lane < n) ? a[k * 32 + lane] : 0x7fffffff;
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < SORT_PER_LANE; ++k) {
-            const int nxt = __shfl_down_sync(0xffffffffu, v[k], 1);
-            const int wrap = (k + 1 < SORT_PER_LANE) ? __shfl_sync(0xffffffffu, v[k + 1 < SORT_PER_LANE ? k + 1 : k], 0) : 0x7fffffff;
-            bad |= v[k] > (lane < 31 ? nxt : wrap);
-        }
-        if (__ballot_sync(0xffffffffu, bad) == 0u) continue;
-        int r[SORT_PER_LANE];
-#pragma unroll
-        for (int k = 0; k < SORT_PER_LANE; ++k) r[k] = 0;
-        const int groups = (n + 31) >> 5;
-#pragma unroll
-        for (int kk = 0; kk < SORT_PER_LANE; ++kk) {
-            if (kk < groups) {
-                for (int j = 0; j < 32; ++j) {
-                    const int x = __shfl_sync(0xffffffffu, v[kk], j);
-#pragma unroll
-                    for (int k = 0; k < SORT_PER_LANE; ++k) r[k] += (x < v[k]);
-                }
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < SORT_PER_LANE; ++k)
-            if (k * 32 + lane < n) a[r[k]] = v[k];          // ids are unique inside one list
+        if (n <= 32) warp_rank_sort<1>(a, n, a, lane);
+        else if (n <= 64) warp_rank_sort<2>(a, n, a, lane);
+        else if (n <= 128) warp_rank_sort<4>(a, n, a, lane);
+        else warp_rank_sort<8>(a, n, a, lane);
     }
 
     // ---- pass B: longer lists, the whole CTA per list.  First every thread looks at one entry
@@ -624,7 +599,7 @@ bool binning_fits_one_cta_per_view(int nf, int R) {
 
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
     const int nt = a.ntx * a.ntx;
-    if (a.one_cta_per_view && binning_fits_one_cta_per_view(a.nf, a.R)) {
+    if (a.one_cta_per_view && a.tile_shift == 4 && binning_fits_one_cta_per_view(a.nf, a.R)) {
         static bool attr_set[64] = {false};
         const size_t smem = (4 * (size_t)nt + BINVIEW_SMEM_PAIRS) * sizeof(int);
         int dev = 0;
@@ -675,7 +650,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
         const unsigned blocks = (unsigned)((nface + 255) / 256);
         ProfScope p(PROF_SETUP, stream);
         k_setup_count<<<blocks, 256, 0, stream>>>(a.verts, a.faces, a.B, a.nv, a.nf, a.R,
-                                                  a.draw_backside, a.rec, a.tile_count, a.ntx, a.hdr);
+                                                  a.draw_backside, a.rec, a.tile_count, a.ntx, a.tile_shift, a.hdr);
     }
     {
         ProfScope p(PROF_SCAN, stream);
@@ -686,7 +661,7 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
         const unsigned blocks = (unsigned)((nface + 255) / 256);
         {
             ProfScope p(PROF_SCATTER, stream);
-            k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_cursor, a.pairs,
+            k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_shift, a.tile_cursor, a.pairs,
                                                   a.pair_capacity, a.hdr);
         }
         ProfScope p(PROF_SORT_LONG, stream);

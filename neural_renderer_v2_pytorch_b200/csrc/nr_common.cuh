@@ -19,6 +19,9 @@ constexpr int WARP_BH = 4;
 // nrRasterConfig.flags (include/nr_b200.h)
 constexpr int FLAG_RGB = 1, FLAG_SIL = 2, FLAG_DEPTH = 4, FLAG_BACKSIDE = 8, FLAG_AA = 16,
               FLAG_DETERMINISTIC = 32;
+// Dense meshes (hundreds of faces per 16x16 tile) are binned into 8x8 tiles instead: four times shorter
+// lists to sort and to walk (general binning path and the FINE raster variants only).
+constexpr int FINE_TILE = 8;
 
 // Workspace header (device side). Layout shared by all kernels.
 struct BinHeader {

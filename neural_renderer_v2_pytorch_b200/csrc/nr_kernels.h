@@ -33,6 +33,7 @@ struct BinningArgs {
     int32_t *tile_list;     // [TILE_LIST_HDR + 4 * TILE_CLASSES * B * ntx * ntx] ints, header zeroed here
     int sm_count;
     int one_cta_per_view;   // allow the single-kernel small-mesh path (k_bin_view)
+    int tile_shift;         // log2 of the tile edge: 4 (16x16), or 3 (8x8, general path only); ntx counts these tiles
 };
 bool binning_fits_one_cta_per_view(int nf, int R);
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
@@ -58,6 +59,7 @@ struct RasterArgs {
     const int32_t *faces;   // [nf, 3] vertex ids (null: 3f..3f+2), only read when lights are on
     int nv;
     LightArgs lights;
+    int fine;               // 8x8 tiles (ntx and the tile list are in those units)
     int sparse_maps;        // fim / internal only where the backward reads them (see NR_SPARSE_MAPS)
     // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
     int num_zero;

@@ -99,10 +99,11 @@ __device__ __forceinline__ float background_value(const RasterArgs &a, int b, in
 // `sparse`: write only what nr_rasterize_backward reads, i.e. not the face index of an empty tile, and
 // its internal-resolution image (anti-aliasing) only when a neighbouring tile is non-empty (the stencil
 // of a foreground pixel reaches one pixel into the next tile).
-template <bool AA, bool FULL>
+template <bool AA, bool FULL, bool FINE>
 __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane, bool sparse) {
     const int R = a.R, S = a.S, C = a.C;
     constexpr bool aa = AA;
+    constexpr int TSZ = FINE ? FINE_TILE : TILE;
     bool need_fim = true, need_internal = true;
     if (sparse) {
         need_fim = false;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
             need_internal = any != 0;
         }
     }
-    if (!FULL || ((R & 15) == 0 && !a.lights.backgrounds)) {
+    if (!FINE && (!FULL || ((R & 15) == 0 && !a.lights.backgrounds))) {
         // vector path: a tile row is 64 aligned bytes in every plane; the flipped tile is again a tile
         const int r = lane >> 2, q = (lane & 3) * 4;
         const int4 m1 = make_int4(-1, -1, -1, -1);
@@ -149,8 +150,8 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
     }
     // (the launcher sends everything the vector path cannot do to the FULL variant)
     if constexpr (FULL) {
-    for (int p = lane; p < TILE * TILE; p += 32) {
-        const int xi = tx * TILE + (p & 15), yi = ty * TILE + (p >> 4);
+    for (int p = lane; p < TSZ * TSZ; p += 32) {
+        const int xi = tx * TSZ + (p & (TSZ - 1)), yi = ty * TSZ + p / TSZ;
         if (xi >= R || yi >= R) continue;
         if (need_fim) a.fim[((size_t)b * R + yi) * R + xi] = -1;
         if (!a.images) continue;
@@ -182,9 +183,11 @@ constexpr int RASTER_WARPS = TILE_THREADS / 32;
 // backgrounds, the weight / depth maps of rasterize_maps, resolutions that are no multiple of 16).
 // The plain variants leave that code out, which halves their size: at 75 KB the one-size kernel spent
 // as many issue slots waiting for instructions as for memory.
-template <bool RGB, bool AA, bool FULL>
+template <bool RGB, bool AA, bool FULL, bool FINE>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_raster(const RasterArgs a) {
+    // a tile is 16x16 pixels = 8 warp blocks (8x4 each), or in the FINE variants 8x8 = 2 blocks
+    constexpr int TSZ = FINE ? FINE_TILE : TILE, BLK_SHIFT = FINE ? 1 : 3, BLKS = 1 << BLK_SHIFT;
     __shared__ float4 s_rec[RASTER_WARPS][32][4];
     __shared__ uint2 s_bb[RASTER_WARPS][32];
 
@@ -195,7 +198,7 @@ k_raster(const RasterArgs a) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int R = a.R;
     const TileList tl = open_tile_list(a.tile_list, a.B * a.ntx * a.ntx);
-    const int items = tl.total * RASTER_WARPS;
+    const int items = tl.total * BLKS;
     constexpr bool aa = AA;
     const bool has_bg = FULL && RGB && a.lights.backgrounds != nullptr;
     const bool pow2 = (R & (R - 1)) == 0;
@@ -230,7 +233,7 @@ k_raster(const RasterArgs a) {
                 ty = tt / a.ntx;
                 tx = tt - ty * a.ntx;
             }
-            fill_empty_tile<AA, FULL>(a, b, tx, ty, lane, a.sparse_maps != 0);
+            fill_empty_tile<AA, FULL, FINE>(a, b, tx, ty, lane, a.sparse_maps != 0);
             return;
         }
         int j = i - all_tiles;
@@ -263,12 +266,12 @@ k_raster(const RasterArgs a) {
         if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
         if (first < fill_items) do_fill(first);
     for (int item = first; item < min(first + GRAB, items); ++item) {
-        const int4 e0 = tile_entry(tl, item >> 3);
-        const int sub = item & 7;
+        const int4 e0 = tile_entry(tl, item >> BLK_SHIFT);
+        const int sub = item & (BLKS - 1);
         const int b = e0.x, n = overflow ? a.nf : e0.w;
         const int32_t *list = a.pairs + e0.z;
-        const int wx0 = (e0.y & 0xffff) * TILE + (sub & 1) * WARP_BW, wx1 = wx0 + WARP_BW - 1;
-        const int wy0 = (e0.y >> 16) * TILE + (sub >> 1) * WARP_BH, wy1 = wy0 + WARP_BH - 1;
+        const int wx0 = (e0.y & 0xffff) * TSZ + (FINE ? 0 : (sub & 1) * WARP_BW), wx1 = wx0 + WARP_BW - 1;
+        const int wy0 = (e0.y >> 16) * TSZ + (FINE ? sub : (sub >> 1)) * WARP_BH, wy1 = wy0 + WARP_BH - 1;
         const int xi = wx0 + (lane & 7), yi = wy0 + (lane >> 3);
         const bool valid = (xi < R) && (yi < R);
         const float xp = pow2 ? __fmul_rn((float)(2 * xi + 1 - R), invR) : pix_center(xi, R);
@@ -511,16 +514,25 @@ cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     // everything optional goes to the FULL variants
     const bool full = a.lights.num > 0 || a.lights.backgrounds || a.wmap || a.dmap || !a.images || (a.R & 15);
     ProfScope p(PROF_RASTER, stream);
+    if (a.fine) {       // dense meshes: the full-featured kernels over 8x8 tiles
+        switch ((rgb ? 1 : 0) | (aa ? 2 : 0)) {
+            case 0: k_raster<false, false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+            case 1: k_raster<true, false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+            case 2: k_raster<false, true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+            default: k_raster<true, true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        }
+        return cudaGetLastError();
+    }
     const int variant = (rgb ? 1 : 0) | (aa ? 2 : 0) | (full ? 4 : 0);
     switch (variant) {
-        case 0: k_raster<false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 1: k_raster<true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 2: k_raster<false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 3: k_raster<true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 4: k_raster<false, false, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 5: k_raster<true, false, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 6: k_raster<false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        default: k_raster<true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 0: k_raster<false, false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 1: k_raster<true, false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 2: k_raster<false, true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 3: k_raster<true, true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 4: k_raster<false, false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 5: k_raster<true, false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 6: k_raster<false, true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        default: k_raster<true, true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
     }
     return cudaGetLastError();
 }

@@ -26,6 +26,13 @@ DEPTH_MIN_DELTA = 1e-4      # rasterize.py:35
 # RasterizeHyperparam(...).deterministic = True.  Costs one int64 scratch buffer per backward.
 DETERMINISTIC = False
 
+# test hook: bin into 8x8 tiles (dense-mesh mode of the general path) whatever the statistics say
+FORCE_FINE_TILES = False
+
+# Tile lists longer than this (nrBinStats.max_tile_faces of an earlier call) switch a shape that is binned
+# by the general path to 8x8 tiles.
+FINE_TILES_ABOVE = 192
+
 # test hook: always bin with the general multi-kernel path (large meshes) instead of the one-kernel path
 FORCE_GENERAL_BINNING = False
 
@@ -70,7 +77,9 @@ class _Scratch:
         self.pending = False
         self.overflows = 0
         self.general_binning = set()        # (nf, R) whose views outgrew the one-kernel small-mesh binning
+        self.fine_tiles = set()             # (nf, R) dense enough for 8x8 tiles (general path only)
         self.last_shape = None
+        self.last_small = True
         ev = ctypes.c_void_p()
         _lib.check(_lib.lib().nr_event_create(ctypes.byref(ev)), "nr_event_create")
         self.event = ev
@@ -93,7 +102,9 @@ class _Scratch:
         elif L.nr_event_query(self.event) != 1:
             return
         self.pending = False
-        total, _max_tile, overflow, _bad = self.stats.tolist()
+        total, max_tile, overflow, _bad = self.stats.tolist()
+        if max_tile > FINE_TILES_ABOVE and self.last_shape is not None and not self.last_small:
+            self.fine_tiles.add(self.last_shape)
         if overflow:
             self.overflows += 1
             self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
@@ -173,7 +184,18 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
         wmap = torch.empty((B, R, R, 3), dtype=torch.float32, device=dev) if want_maps else None
         dmap = torch.empty((B, R, R), dtype=torch.float32, device=dev) if want_maps else None
-        ntx = (R + 15) // 16
+        # which binning this call takes: one kernel per view (small meshes), the general path, or the
+        # general path over 8x8 tiles (dense meshes); the last two are learnt from earlier calls' statistics
+        shape = (cfg.num_faces, R)
+        general = shape in sc.general_binning or FORCE_GENERAL_BINNING
+        small = cfg.num_faces <= 8192 and ((R + 15) // 16) ** 2 <= 4096 and not general
+        fine = FORCE_FINE_TILES or (not small and shape in sc.fine_tiles)
+        if general:
+            cfg.flags |= _lib.NR_GENERAL_BINNING
+        if fine:
+            cfg.flags |= _lib.NR_FINE_TILES
+        tile = 8 if fine else 16
+        ntx = (R + tile - 1) // tile
         tile_list = torch.empty(8 + 16 * B * ntx * ntx, dtype=torch.int32, device=dev)
         capacity = max(sc.pair_capacity, 4 * B * cfg.num_faces + 4096)
         if FORCE_PAIR_CAPACITY is not None:
@@ -190,12 +212,10 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         base = ws.data_ptr()
         aligned = (base + 255) & ~255
         track = not sc.pending and not capturing
-        if (cfg.num_faces, R) in sc.general_binning or FORCE_GENERAL_BINNING:
-            cfg.flags |= _lib.NR_GENERAL_BINNING
-        if sparse and not want_maps:
+        if sparse and not want_maps and not fine:
             cfg.flags |= _lib.NR_SPARSE_MAPS     # fim / internal image are only handed to the backward
         if track:
-            sc.last_shape = (cfg.num_faces, R)
+            sc.last_shape, sc.last_small = shape, small
         rc = L.nr_rasterize_forward(
             ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
@@ -205,7 +225,8 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         _lib.check(rc, "nr_rasterize_forward")
         if track:
             sc.pending = True
-        return images, internal, fim, wmap, dmap, tile_list
+        # with 8x8 tiles the list is of no use to the backward (it walks 16x16 tiles)
+        return images, internal, fim, wmap, dmap, (None if fine else tile_list)
 
 
 _validated_faces = {}

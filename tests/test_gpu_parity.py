@@ -82,6 +82,25 @@ def test_golden_case(nr, name):
         grad_close(vt.grad.cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
 
 
+@pytest.mark.parametrize("name", ["case_rgba_64", "case_rgba_aa_32", "case_depth_aa_32", "case_sil_cull_64"])
+def test_golden_case_with_fine_tiles(nr, name):
+    """The dense-mesh mode (general binning over 8x8 tiles, backward over all 16x16 tiles) against the
+    same reference fixtures: images and every gradient."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    rz.FORCE_FINE_TILES = True
+    try:
+        images, v, tex, vt, maps = run_cuda(nr, d)
+    finally:
+        rz.FORCE_FINE_TILES = False
+    assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
+    np.testing.assert_allclose(images.detach().cpu().numpy(), d["images"], rtol=1e-5, atol=1e-6)
+    grad_close(v.grad.cpu().numpy(), d["grad_vertices"], "grad_vertices")
+    if tex is not None:
+        grad_close(tex.grad.cpu().numpy(), d["grad_textures"], "grad_textures")
+        grad_close(vt.grad.cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
+
+
 @pytest.mark.parametrize("name", ["lit_rgb_48", "lit_rgb_aa_24"])
 def test_lights_golden(nr, name):
     """Directional + Ambient + Specular lights (rasterize.py:252-283) fused into the kernels vs the
@@ -176,16 +195,16 @@ def _check_vs_oracle(nr, faces_np, R, **kw):
     B, nf = faces_np.shape[:2]
     v = torch.from_numpy(np.ascontiguousarray(faces_np, dtype=np.float32)).reshape(B, nf * 3, 3).cuda()
     idx = torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3).cuda()
-    for general in (False, True):
-        rz.FORCE_GENERAL_BINNING = general
+    for general, fine in ((False, False), (True, False), (True, True)):
+        rz.FORCE_GENERAL_BINNING, rz.FORCE_FINE_TILES = general, fine
         try:
             hp = nr.RasterizeHyperparam(image_size=R, near=kw.get("near", 0.1), far=kw.get("far", 100.0), anti_aliasing=False,
                                         draw_backside=kw.get("backside", True), draw_rgb=False, draw_depth=False)
             maps = nr.rasterize_maps(v, idx, nr.RasterizeParam(), hp)
         finally:
-            rz.FORCE_GENERAL_BINNING = False
-        assert np.array_equal(maps["face_index_map"].cpu().numpy(), want), "fused forward (general=%s): face_index_map" % general
-        assert np.array_equal(maps["weight_map"].cpu().numpy(), want_wm), "fused forward (general=%s): weight_map" % general
+            rz.FORCE_GENERAL_BINNING = rz.FORCE_FINE_TILES = False
+        assert np.array_equal(maps["face_index_map"].cpu().numpy(), want), "fused forward (general=%s, fine=%s): face_index_map" % (general, fine)
+        assert np.array_equal(maps["weight_map"].cpu().numpy(), want_wm), "fused forward (general=%s, fine=%s): weight_map" % (general, fine)
         assert np.array_equal(maps["images"][:, 0].flip(1, 2).cpu().numpy(), (want >= 0).astype(np.float32))
     return fim
 
