@@ -324,6 +324,8 @@ def run_ours(args):
     cnt = (ctypes.c_int32 * _lib.NR_PROF_SLOTS)()
     L.nr_profile_collect(ms, cnt)
     kern = {n: (ms[i] / cnt[i]) for i, n in enumerate(_lib.PROF_SLOT_NAMES) if cnt[i]}
+    if "setup_count" in kern and "scan_tiles" not in kern:
+        kern["bin_view"] = kern.pop("setup_count")      # small meshes: the one-kernel cluster binning uses this slot
     # kernels of this library per step (memset nodes not counted)
     launches_per_step = sum(cnt[i] for i, n in enumerate(_lib.PROF_SLOT_NAMES) if n != "memset") / args.steps
 
@@ -482,13 +484,17 @@ def cpu_baseline_sample(workload, budget_s=12.0):
     oracle_step(inp, w, 1)
     t1 = time.perf_counter() - t0
     views = int(max(1, min(w["views"], budget_s / max(t1, 1e-3))))
-    t0 = time.perf_counter()
-    oracle_step(inp, w, views)
-    t = time.perf_counter() - t0
-    return {"value": round(views * w["S"] ** 2 / 1e6 / t, 3), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d views of %s, one fwd+bwd, %.1f s; C z-buffer/weight-map restatement (OpenMP) + "
+    reps, t0 = 0, time.perf_counter()
+    while True:                                 # about budget_s seconds of CPU work
+        oracle_step(inp, w, views)
+        reps += 1
+        t = time.perf_counter() - t0
+        if t >= budget_s * 0.8 or reps >= 16:
+            break
+    return {"value": round(reps * views * w["S"] ** 2 / 1e6 / t, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d x (%d of %d views of %s, one fwd+bwd), %.1f s; C z-buffer/weight-map restatement (OpenMP) + "
                       "torch-CPU stages; the reference itself has no CPU z-buffer (rasterize_cuda.cpp:60-61)"
-                      % (views, w["views"], workload, t)}
+                      % (reps, views, w["views"], workload, t)}
 
 
 def run_reference(args):

@@ -115,9 +115,10 @@ __device__ __forceinline__ void sample_texture_backward(const float *__restrict_
         if ((unsigned)tap[t] >= (unsigned)T) tap[t] = -1;
         d[t] = 0.f;
         if (tap[t] >= 0) {
+            const float *pt = tex_b + tap[t];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float tv = __ldg(tex_b + (size_t)c * T + tap[t]);
+                const float tv = __ldg(pt + c * T);
                 d[t] += g[c] * tv;
                 rgb_tex[c] += tw[t] * tv;
             }
@@ -184,8 +185,8 @@ __device__ __forceinline__ bool run_reduce(int key, bool valid, float (&v)[N], i
 // depends on arrival order; in deterministic mode the value is rounded ONCE to 64-bit fixed point
 // (value * 2^k) and added with integer atomics, which are exactly associative: the sum is bit-identical
 // from run to run whatever the order.  The warp-level run sums in front of it have a fixed order.
-template <bool DET>
-__device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, size_t idx, float v, float scale) {
+template <bool DET, class Index>
+__device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, Index idx, float v, float scale) {
     if (DET) {
         atomicAdd(reinterpret_cast<unsigned long long *>(dst_i + idx),
                   (unsigned long long)__double2ll_rn((double)v * (double)scale));
@@ -234,22 +235,24 @@ k_backward(const BackwardArgs a) {
         const float *Gb = a.grad_images + (size_t)b * C * S * S;
         const float gs = aa ? 0.25f : 1.f;   // 2x2 mean backward (rasterize.py:323-328), exact
         const int sh = aa ? 1 : 0;
-        const size_t i_c = (size_t)u_ * R + v_, i_yp = (size_t)u_yp * R + v_, i_ym = (size_t)u_ym * R + v_;
-        const size_t i_xp = (size_t)u_ * R + v_xp, i_xm = (size_t)u_ * R + v_xm;
-        const size_t g_c = (size_t)(u_ >> sh) * S + (v_ >> sh), g_yp = (size_t)(u_yp >> sh) * S + (v_ >> sh);
-        const size_t g_ym = (size_t)(u_ym >> sh) * S + (v_ >> sh), g_xp = (size_t)(u_ >> sh) * S + (v_xp >> sh);
-        const size_t g_xm = (size_t)(u_ >> sh) * S + (v_xm >> sh);
+        // one 64-bit pointer per array (this pixel, channel 0); neighbours and channels are 32-bit element
+        // offsets from it (R <= 32768, so a plane has < 2^31 elements)
+        const float *pI = Ib + (size_t)u_ * R + v_;
+        const float *pG = Gb + (size_t)(u_ >> sh) * S + (v_ >> sh);
+        const int dI_yp = (u_yp - u_) * R, dI_ym = (u_ym - u_) * R, dI_xp = v_xp - v_, dI_xm = v_xm - v_;
+        const int dG_yp = ((u_yp >> sh) - (u_ >> sh)) * S, dG_ym = ((u_ym >> sh) - (u_ >> sh)) * S;
+        const int dG_xp = (v_xp >> sh) - (v_ >> sh), dG_xm = (v_xm >> sh) - (v_ >> sh);
+        const int planeI = R * R, planeG = S * S;
         float ry_i = 0.f, ry_m = 0.f, ly_m = 0.f, ly_i = 0.f, rx_i = 0.f, rx_m = 0.f, lx_m = 0.f, lx_i = 0.f;
 #pragma unroll
         for (int c = 0; c < (CT ? CT : 5); ++c) {
             if (c < C) {
-                const float *Ic = Ib + (size_t)c * R * R;
-                const float *Gc = Gb + (size_t)c * S * S;
-                const float ic = __ldg(Ic + i_c), iyp = __ldg(Ic + i_yp), iym = __ldg(Ic + i_ym);
-                const float ixp = __ldg(Ic + i_xp), ixm = __ldg(Ic + i_xm);
-                const float gc = __fmul_rn(__ldg(Gc + g_c), gs), gyp = __fmul_rn(__ldg(Gc + g_yp), gs);
-                const float gym = __fmul_rn(__ldg(Gc + g_ym), gs), gxp = __fmul_rn(__ldg(Gc + g_xp), gs);
-                const float gxm = __fmul_rn(__ldg(Gc + g_xm), gs);
+                const float *Ic = pI + c * planeI, *Gc = pG + c * planeG;
+                const float ic = __ldg(Ic), iyp = __ldg(Ic + dI_yp), iym = __ldg(Ic + dI_ym);
+                const float ixp = __ldg(Ic + dI_xp), ixm = __ldg(Ic + dI_xm);
+                const float gc = __fmul_rn(__ldg(Gc), gs), gyp = __fmul_rn(__ldg(Gc + dG_yp), gs);
+                const float gym = __fmul_rn(__ldg(Gc + dG_ym), gs), gxp = __fmul_rn(__ldg(Gc + dG_xp), gs);
+                const float gxm = __fmul_rn(__ldg(Gc + dG_xm), gs);
                 gcen[c] = gc;
                 // differentiation.py:19-29; a clamped (out-of-range) neighbour equals the centre, so its
                 // difference is exactly zero and the term vanishes like the zero padding does
@@ -390,10 +393,12 @@ k_backward(const BackwardArgs a) {
                 const size_t o = (size_t)b * a.nv * 3;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
+                    const size_t ok = o + 3 * (size_t)vid[k];
+                    float *pf = a.grad_verts + ok;
+                    long long *pi = DET ? a.det_verts + ok : nullptr;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (vg[3 * k + c] != 0.f)
-                            accumulate<DET>(a.grad_verts, a.det_verts, o + 3 * (size_t)vid[k] + c, vg[3 * k + c], a.det_scale);
+                        if (vg[3 * k + c] != 0.f) accumulate<DET>(pf, pi, c, vg[3 * k + c], a.det_scale);
                 }
             }
         }
@@ -408,10 +413,11 @@ k_backward(const BackwardArgs a) {
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     if (tap[t] < 0) continue;
+                    float *pf = a.grad_tex + o + tap[t];
+                    long long *pi = DET ? a.det_tex + o + tap[t] : nullptr;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (tg[t * 3 + c] != 0.f)
-                            accumulate<DET>(a.grad_tex, a.det_tex, o + c * T + tap[t], tg[t * 3 + c], a.det_scale);
+                        if (tg[t * 3 + c] != 0.f) accumulate<DET>(pf, pi, c * (int)T, tg[t * 3 + c], a.det_scale);
                 }
             }
         }

@@ -33,11 +33,12 @@ __device__ __forceinline__ void sample_texture(const float *__restrict__ tex_b, 
     // IndexError in the reference and reads as zero here.
     const bool ok1 = (unsigned)i1 < (unsigned)T, ok2 = (unsigned)i2 < (unsigned)T;
     const bool ok3 = (unsigned)i3 < (unsigned)T, ok4 = (unsigned)i4 < (unsigned)T;
+    const float *p1 = tex_b + i1, *p2 = tex_b + i2, *p3 = tex_b + i3, *p4 = tex_b + i4;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float *p = tex_b + (size_t)c * T;
-        const float t1 = ok1 ? __ldg(p + i1) : 0.f, t2 = ok2 ? __ldg(p + i2) : 0.f;
-        const float t3 = ok3 ? __ldg(p + i3) : 0.f, t4 = ok4 ? __ldg(p + i4) : 0.f;
+        const int o = c * T;
+        const float t1 = ok1 ? __ldg(p1 + o) : 0.f, t2 = ok2 ? __ldg(p2 + o) : 0.f;
+        const float t3 = ok3 ? __ldg(p3 + o) : 0.f, t4 = ok4 ? __ldg(p4 + o) : 0.f;
         rgb[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, t1), __fmul_rn(w2, t2)), __fmul_rn(w3, t3)),
                            __fmul_rn(w4, t4));
     }
@@ -189,7 +190,7 @@ k_raster(const RasterArgs a) {
     // a tile is 16x16 pixels = 8 warp blocks (8x4 each), or in the FINE variants 8x8 = 2 blocks
     constexpr int TSZ = FINE ? FINE_TILE : TILE, BLK_SHIFT = FINE ? 1 : 3, BLKS = 1 << BLK_SHIFT;
     __shared__ float4 s_rec[RASTER_WARPS][32][4];
-    __shared__ uint2 s_bb[RASTER_WARPS][32];
+    __shared__ uint32_t s_bb[RASTER_WARPS][32];
 
     // If the pair list did not fit the workspace, the lists are unusable: every block then scans ALL
     // faces of its view (the records are complete regardless), which is the reference's own loop with
@@ -205,7 +206,7 @@ k_raster(const RasterArgs a) {
     const float invR = 1.f / (float)R;          // exact for power-of-two R
     const unsigned lt_mask = (1u << lane) - 1u;
     float4 (*my_rec)[4] = s_rec[wid];
-    uint2 *my_bb = s_bb[wid];
+    uint32_t *my_bb = s_bb[wid];
 
     // ---- fill items (stores only), interleaved with the raster items: claim i also performs fill item i,
     // so the fills drain to HBM all along the kernel instead of in one burst that would stall every warp
@@ -324,26 +325,30 @@ k_raster(const RasterArgs a) {
                 my_rec[slot][1] = make_float4(x2, y2, __fsub_rn(x1, x0), __fsub_rn(y1, y0));
                 my_rec[slot][2] = make_float4(__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(x0, x2), __fsub_rn(y0, y2));
                 my_rec[slot][3] = make_float4(z0, z1, z2, __int_as_float(fid));
-                my_bb[slot] = make_uint2(__float_as_uint(q2.y), __float_as_uint(q2.z));
+                // the face's pixel box (:94-97, exact by construction) as a bit mask over this block's 32
+                // pixels (bit = lane): the columns / rows it covers, relative to the block origin
+                const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
+                const int c0 = max((int)(bx & 0xffff) - wx0, 0), c1 = min((int)(bx >> 16) - wx0, WARP_BW - 1);
+                const int r0 = max((int)(by & 0xffff) - wy0, 0), r1 = min((int)(by >> 16) - wy0, WARP_BH - 1);
+                const uint32_t cols = ((2u << c1) - 1u) & ~((1u << c0) - 1u);          // 8 bits
+                const uint32_t rows = ((2u << r1) - 1u) & ~((1u << r0) - 1u);          // 4 bits
+                my_bb[slot] = cols * ((rows * 0x00204081u) & 0x01010101u);              // row r -> bits 8r .. 8r+7
             }
             __syncwarp();
             const int nh = __popc(m);
             // ---- phase 1: coverage of every surviving face, one bit per face (cheap, all lanes)
             unsigned inside = 0u;
+            // (branch-free: at least one lane of the block is inside every surviving face's pixel box, so the
+            // warp executes the edge functions anyway)
             for (int j = 0; j < nh; ++j) {
-                const uint2 bb = my_bb[j];
-                // :94-97, exact by construction of the pixel box
-                if (xi < (int)(bb.x & 0xffff) || xi > (int)(bb.x >> 16) || yi < (int)(bb.y & 0xffff) ||
-                    yi > (int)(bb.y >> 16))
-                    continue;
+                const bool in_box = (my_bb[j] >> lane) & 1u;
                 const float4 A = my_rec[j][0], Bq = my_rec[j][1], Cq = my_rec[j][2];
                 // :107-116
                 const float c1 = __fmaf_rn(__fsub_rn(yp, A.y), Bq.z, -__fmul_rn(Bq.w, __fsub_rn(xp, A.x)));
                 const float c2 = __fmaf_rn(__fsub_rn(yp, A.w), Cq.x, -__fmul_rn(Cq.y, __fsub_rn(xp, A.z)));
-                if (__fmul_rn(c1, c2) < 0.f) continue;
                 const float c3 = __fmaf_rn(__fsub_rn(yp, Bq.y), Cq.z, -__fmul_rn(Cq.w, __fsub_rn(xp, Bq.x)));
-                if (__fmul_rn(c2, c3) < 0.f) continue;
-                inside |= 1u << j;
+                const bool rejected = (__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f);
+                if (in_box && !rejected) inside |= 1u << j;
             }
             // ---- phase 2: every lane walks ITS OWN covering faces in list order (the z-test is
             // sequential per pixel only), so lanes evaluate different faces at the same time and the
@@ -381,10 +386,14 @@ k_raster(const RasterArgs a) {
                 a.fim[((size_t)b * R + yi) * R + xi] = -1;
                 if (!FULL || a.images) {
                     const int u_ = R - 1 - yi, v_ = R - 1 - xi, C = a.C;
-                    float *full = aa ? a.internal : a.images;
-                    for (int c = 0; c < C; ++c) full[(((size_t)b * C + c) * R + u_) * R + v_] = 0.f;
-                    if (aa && !(xi & 1) && !(yi & 1))
-                        for (int c = 0; c < C; ++c) a.images[(((size_t)b * C + c) * a.S + (u_ >> 1)) * a.S + (v_ >> 1)] = 0.f;
+                    float *full = (aa ? a.internal : a.images) + ((size_t)b * C * R + u_) * R + v_;
+                    const int plane = R * R;
+                    for (int c = 0; c < C; ++c) full[c * plane] = 0.f;
+                    if (aa && !(xi & 1) && !(yi & 1)) {
+                        float *half = a.images + ((size_t)b * C * a.S + (u_ >> 1)) * a.S + (v_ >> 1);
+                        const int plane_h = a.S * a.S;
+                        for (int c = 0; c < C; ++c) half[c * plane_h] = 0.f;
+                    }
                 }
             }
             continue;
@@ -410,15 +419,16 @@ k_raster(const RasterArgs a) {
         if (!FULL || a.images) {
             const int C = a.C, S = a.S;
             const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
+            // one 64-bit pointer per output (this pixel, channel 0); channel c is a 32-bit plane offset away
+            float *p_full = (aa ? a.internal : a.images) + ((size_t)b * C * R + u_) * R + v_;
+            float *p_half = aa ? a.images + ((size_t)b * C * S + (u_ >> 1)) * S + (v_ >> 1) : nullptr;
+            const int plane_full = R * R, plane_half = S * S;
             // one channel value of this pixel -> images (and the internal-resolution copy under AA)
             auto put = [&](int c, float val) {
                 // background pixels show the background picture (black without one)
                 if (has_bg && !fg && valid) val = background_value<FULL>(a, b, c, u_, v_);
-                if (!aa) {
-                    if (valid) a.images[(((size_t)b * C + c) * R + u_) * R + v_] = val;
-                    return;
-                }
-                if (valid) a.internal[(((size_t)b * C + c) * R + u_) * R + v_] = val;
+                if (valid) p_full[c * plane_full] = val;
+                if (!aa) return;
                 // quad in flipped coordinates: F[2Y][2X] is (yi odd, xi odd); rasterize.py:323-328
                 const float px_ = __shfl_xor_sync(0xffffffffu, val, 1);   // same row, other column
                 const float py_ = __shfl_xor_sync(0xffffffffu, val, 8);   // other row, same column
@@ -427,7 +437,7 @@ k_raster(const RasterArgs a) {
                     // me = (even, even) -> F[2Y+1][2X+1]; py_ = (odd row, even col) -> F[2Y][2X+1]
                     // px_ = (even row, odd col) -> F[2Y+1][2X]; pd_ = (odd, odd) -> F[2Y][2X]
                     const float sum = __fadd_rn(__fadd_rn(__fadd_rn(pd_, px_), py_), val);
-                    a.images[(((size_t)b * C + c) * S + (u_ >> 1)) * S + (v_ >> 1)] = __fmul_rn(sum, 0.25f);
+                    p_half[c * plane_half] = __fmul_rn(sum, 0.25f);
                 }
             };
             int c = 0;
