@@ -195,6 +195,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION (the image's default) prints "NCCL version ..." on stdout, next to the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     B, S = w["views"], w["S"]
