@@ -195,9 +195,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION (the image's default) prints "NCCL version ..." on stdout, next to the JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its "NCCL version ..." banner (NCCL_DEBUG=VERSION / WARN) on stdout, next to the JSON
+        # line; send its log to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[args.workload]
     B, S = w["views"], w["S"]
