@@ -465,7 +465,8 @@ k_bin_view(const float *__restrict__ verts, const int32_t *__restrict__ faces, i
 // the whole CTA with a bitonic network in shared memory.
 constexpr int SORT_WARPS = 8;
 constexpr int SORT_PER_LANE = 8;
-constexpr int SORT_WARP_MAX = 32 * SORT_PER_LANE;     // lists up to this length: one warp each
+constexpr int SORT_WARP_MAX = 32 * SORT_PER_LANE;     // lists up to this length: one warp each, in registers
+constexpr int WARP_SORT_SMEM = 1024;                  // ... up to this length: one warp each, in shared memory
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict__ pairs,
              const BinHeader *__restrict__ hdr) {
@@ -490,6 +491,49 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
         else warp_rank_sort<8>(a, n, a, lane);
     }
 
+    // ---- pass A2: lists of 257 .. 1024 ids, still one warp per list (eight lists per CTA at a time, no
+    // CTA barrier): bitonic network in the warp's 1024-id slice of shared memory, same direction over the
+    // virtual power-of-two length (indices >= n behave as +inf and never move)
+    static_assert(SMEM_SORT_CAP >= SORT_WARPS * WARP_SORT_SMEM, "one slice per warp");
+    for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
+        const int4 e = tile_entry(tl, w);
+        const int n = e.w;
+        if (n <= SORT_WARP_MAX || n > WARP_SORT_SMEM) continue;
+        int32_t *a = pairs + e.z;
+        int *s = s_ids + wid * WARP_SORT_SMEM;
+        for (int i = lane; i < n; i += 32) s[i] = a[i];
+        __syncwarp();
+        int lg = 9;
+        while ((1 << lg) < n) ++lg;
+        const int half = 1 << (lg - 1);
+        for (int kk = 1; kk <= lg; ++kk) {
+            const int k = 1 << kk;
+            for (int i = lane; i < half; i += 32) {
+                const int blk = i >> (kk - 1), off = i & ((k >> 1) - 1);
+                const int lo = (blk << kk) + off, hi = (blk << kk) + k - 1 - off;
+                if (hi < n) {
+                    const int x = s[lo], y = s[hi];
+                    if (x > y) { s[lo] = y; s[hi] = x; }
+                }
+            }
+            __syncwarp();
+            for (int jj = kk - 2; jj >= 0; --jj) {
+                const int j = 1 << jj;
+                for (int i = lane; i < half; i += 32) {
+                    const int lo = ((i >> jj) << (jj + 1)) + (i & (j - 1)), hi = lo + j;
+                    if (hi < n) {
+                        const int x = s[lo], y = s[hi];
+                        if (x > y) { s[lo] = y; s[hi] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < n; i += 32) a[i] = s[i];
+        __syncwarp();
+    }
+    __syncthreads();
+
     // ---- pass B: longer lists, the whole CTA per list.  First every thread looks at one entry
     // of this CTA's share (independent loads), the long ones are compacted, then sorted one by one
     // with a same-direction bitonic network over a virtual power-of-two length (indices >= n behave
@@ -501,7 +545,7 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
         const int w = (base + tid) * (int)gridDim.x + (int)blockIdx.x;
         if (w < count) {
             const int n = tile_entry(tl, w).w;
-            if (n > SORT_WARP_MAX && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
+            if (n > WARP_SORT_SMEM && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
         }
         __syncthreads();
         const int nlong = s_nlong;

@@ -109,3 +109,22 @@ def test_config4_window_against_the_oracle(nr):
         got = fim[b, y0:y0 + n, x0:x0 + n].cpu().numpy()
         assert np.array_equal(got, want), "%d / %d window pixels differ" % ((got != want).sum(), got.size)
         assert (got >= 0).mean() > 0.3
+
+
+def test_many_views_more_than_one_wave_of_binning_clusters(nr):
+    """150 views (more binning clusters than SMs, so they run in waves): every view must equal the
+    same view rendered alone."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "teapot.npz"))
+    B, S = 150, 64
+    g = torch.Generator().manual_seed(150)
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20, torch.rand(B, generator=g) * 360)
+    vs = nr.perspective(nr.look_at(vw, eye)).cuda()
+    faces = torch.from_numpy(d["faces"]).cuda()
+    hp = lambda: nr.RasterizeHyperparam(image_size=S, anti_aliasing=False)
+    with torch.no_grad():
+        all_views = nr.rasterize_silhouettes(vs, faces, nr.RasterizeParam(), hp())
+        for b in (0, 1, 63, 64, 127, 128, 149):
+            one = nr.rasterize_silhouettes(vs[b:b + 1], faces, nr.RasterizeParam(), hp())
+            assert torch.equal(all_views[b:b + 1], one), b
+    assert 0.02 < float(all_views.mean()) < 0.6

@@ -300,6 +300,16 @@ def test_long_tile_lists(nr):
     _check_vs_oracle(nr, f, 64)
 
 
+@pytest.mark.parametrize("nf", [130, 300, 700, 1500])
+def test_mid_size_tile_lists(nr, nf):
+    """130 .. 1500 faces in one tile: every size class of the per-tile sort (registers up to 256 ids,
+    one warp in shared memory up to 1024, the whole CTA beyond) in all three binning modes."""
+    rng = np.random.RandomState(nf)
+    f = random_triangles(2, nf, nf, size=0.02)
+    f[..., :2] = f[..., :2] * 0.05 + rng.uniform(-0.02, 0.02)     # everything inside one 16x16 tile
+    _check_vs_oracle(nr, f, 64)
+
+
 def test_pair_list_overflow_falls_back_on_device(nr):
     """With no room for the (tile, face) pairs the forward must still be exact (every block scans all
     faces of its view) and the host must grow the capacity from the lazily read statistics."""
