@@ -1,6 +1,7 @@
 // nr_backward.cu -- fused backward of the rasterize path.
 //
-// One thread per internal pixel (same 16x16 tiling / 8x4 warp blocks as the forward):
+// Persistent over the forward's non-empty 16x16 tiles; one thread per internal pixel, a warp owns two
+// 16-pixel row segments of the tile (so the pixels of one face form runs in lane order):
 //   1. upstream gradient through the 2x2 anti-aliasing mean, flip and permute
 //      (autograd of rasterize.py:315-328), read straight from grad_images [B,C,S,S];
 //   2. the Differentiation stencil (differentiation.py:13-36, utils.py:75-101) on the

@@ -1,9 +1,10 @@
 // nr_raster.cu -- tile rasterizer with fused shading epilogue.
 //
-// One CTA per (view, 16x16 tile), one thread per pixel.  The tile's face list (ascending face
-// index) is staged through shared memory in chunks of 256 records; each warp owns an 8x4 pixel
-// block, culls the chunk against that block 32 faces at a time (one lane per face, ballot),
-// and only the surviving faces are evaluated per pixel with the reference's arithmetic:
+// Persistent kernel: one WARP owns an 8x4 pixel block of a non-empty tile (16x16, or 8x8 for dense
+// meshes), claimed dynamically from the heavy-first tile list.  It walks the tile's face list
+// (ascending face index) 32 entries at a time: one lane per face culls against the block (pixel box,
+// then a conservative edge-interval test, ballot), the survivors are staged in the warp's slice of
+// shared memory, and only those are evaluated per pixel with the reference's arithmetic:
 //   rasterize_cuda_kernel.cu:94-149  (z-buffer, sequential 1e-4 hysteresis)
 // The epilogue fuses what the reference does in ~60 torch ops and 9*B host round trips:
 //   rasterize_cuda_kernel.cu:246-308 weight map, rasterize.py:100-153 texture sampling,
@@ -172,12 +173,13 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
 }
 
 // Persistent kernel over the non-empty tiles.  The unit of work is one WARP = one 8x4 pixel block
-// of a tile (warp-granular static grid-stride; the 8 warps of a CTA take the 8 blocks of one tile, so
-// the tile's records are shared through L1).  Warps never wait for each other: a block without
-// candidate faces costs one cull pass.  Per 32 faces of the tile list: every lane loads one face
-// record, tests its pixel box against the block, the survivors are compacted (ballot) into this
-// warp's slice of shared memory with their edge deltas, then evaluated per pixel in list order.
-// Background pixels were pre-filled by launch_raster, so only foreground pixels are written.
+// of a tile, claimed with one atomicAdd (the next claim is in flight while the current block is
+// processed); the blocks of a tile are neighbours in the claim order, so its records are shared through
+// L1 / L2.  Warps never wait for each other: a block without candidate faces costs one cull pass.
+// Per 32 faces of the tile list: every lane loads one face record, tests its pixel box against the
+// block, the survivors are compacted (ballot) into this warp's slice of shared memory with their edge
+// deltas and their pixel box as a bit mask over the block, then evaluated per pixel in list order.
+// Every pixel of the block is written (background included), see "output initialisation" above.
 constexpr int RASTER_WARPS = TILE_THREADS / 32;
 
 // Variants: RGB (texture sampling), AA (2x2 mean epilogue), FULL (everything optional: lights,
@@ -256,8 +258,8 @@ k_raster(const RasterArgs a) {
         }
     };
 
-    // dynamic scheduling: a warp claims two adjacent blocks at a time; the next claim is issued
-    // before the current pair is processed so its latency is hidden
+    // dynamic scheduling: a warp claims one block at a time; the next claim is issued before the
+    // current block is processed so its latency is hidden
     constexpr int GRAB = 1;
     int claim = 0;
     if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
