@@ -494,8 +494,12 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
     // ---- pass A2: lists of 257 .. 1024 ids, still one warp per list (eight lists per CTA at a time, no
     // CTA barrier): bitonic network in the warp's 1024-id slice of shared memory, same direction over the
     // virtual power-of-two length (indices >= n behave as +inf and never move)
+    // Only when there are more long lists than warps in the grid (a dense mesh everywhere): with a few
+    // long lists (the limb of a sphere) one warp each would be the critical path, and pass B is faster.
     static_assert(SMEM_SORT_CAP >= SORT_WARPS * WARP_SORT_SMEM, "one slice per warp");
-    for (int w = blockIdx.x * SORT_WARPS + wid; w < count; w += gridDim.x * SORT_WARPS) {
+    const bool many_long = tl.c[0] > (int)gridDim.x * SORT_WARPS;
+    const int warp_sort_max = many_long ? WARP_SORT_SMEM : SORT_WARP_MAX;
+    for (int w = blockIdx.x * SORT_WARPS + wid; many_long && w < count; w += gridDim.x * SORT_WARPS) {
         const int4 e = tile_entry(tl, w);
         const int n = e.w;
         if (n <= SORT_WARP_MAX || n > WARP_SORT_SMEM) continue;
@@ -545,7 +549,7 @@ k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict
         const int w = (base + tid) * (int)gridDim.x + (int)blockIdx.x;
         if (w < count) {
             const int n = tile_entry(tl, w).w;
-            if (n > WARP_SORT_SMEM && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
+            if (n > warp_sort_max && n <= SMEM_SORT_CAP) s_long[atomicAdd(&s_nlong, 1)] = w;
         }
         __syncthreads();
         const int nlong = s_nlong;

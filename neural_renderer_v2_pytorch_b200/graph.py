@@ -30,10 +30,13 @@ def capture_step(step, params=(), warmup=3):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for _ in range(max(warmup, 1)):       # eager runs: size workspaces, validate indices
+        for _ in range(max(warmup, 2)):       # eager runs: size workspaces, validate indices
             for p in params:
                 p.grad = None
             step()
+            # each run sees the bin statistics of the one before it (pair capacity, binning mode), so
+            # the captured step is the settled one
+            side.synchronize()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     for p in params:

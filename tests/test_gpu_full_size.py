@@ -91,6 +91,14 @@ def test_config4_window_against_the_oracle(nr):
     fim = maps["face_index_map"]
     again = nr.rasterize_maps(v, faces, nr.RasterizeParam(), hp)["face_index_map"]
     assert torch.equal(fim, again)
+    # the dense-mesh mode (8x8 tiles; tens of thousands of long lists, sorted one warp each in shared memory)
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    rz.FORCE_FINE_TILES = True
+    try:
+        fine = nr.rasterize_maps(v, faces, nr.RasterizeParam(), hp)["face_index_map"]
+    finally:
+        rz.FORCE_FINE_TILES = False
+    assert torch.equal(fim, fine)
     one = nr.rasterize_maps(v[1:2], faces, nr.RasterizeParam(), hp)["face_index_map"]
     assert torch.equal(fim[1:2], one)
     fv = v[:, faces.long()]                                           # [2, nf, 3, 3]
