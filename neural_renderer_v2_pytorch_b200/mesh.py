@@ -14,14 +14,12 @@ from .load_obj import load_obj
 class Mesh(nn.Module):
     def __init__(self, filename_obj, texture_size=4, normalization=True):
         super().__init__()
-        vertices, faces = load_obj(filename_obj, normalization)
-        self.vertices = torch.as_tensor(vertices)                       # mesh.py:14 (a plain tensor, not a Parameter)
-        self.faces = torch.as_tensor(faces)
-        self.num_vertices = self.vertices.shape[0]
-        self.num_faces = self.faces.shape[0]
-        shape = (self.num_faces, texture_size, texture_size, texture_size, 3)
-        self.textures = nn.Parameter(torch.randn(shape))                # mesh.py:19-20
+        geometry = load_obj(filename_obj, normalization)
+        self.vertices, self.faces = (torch.as_tensor(x) for x in geometry)   # mesh.py:14: plain tensors, not Parameters
+        self.num_vertices, self.num_faces = len(self.vertices), len(self.faces)
         self.texture_size = texture_size
+        # legacy v1 texture cube per face, normal-initialised (mesh.py:19-20)
+        self.textures = nn.Parameter(torch.randn(self.num_faces, *([texture_size] * 3), 3))
 
     def to(self, *args, **kwargs):
         super().to(*args, **kwargs)
@@ -33,11 +31,11 @@ class Mesh(nn.Module):
 
     def get_batch(self, batch_size):
         """Broadcast to a minibatch (mesh.py:28-33); textures go through a sigmoid."""
-        vertices = self.vertices.expand([batch_size] + list(self.vertices.shape))
-        faces = self.faces.expand([batch_size] + list(self.faces.shape))
-        textures = torch.sigmoid(self.textures.expand([batch_size] + list(self.textures.shape)))
-        return vertices, faces, textures
+        def tile(t):
+            return t.unsqueeze(0).expand(batch_size, *t.shape)
+        return tile(self.vertices), tile(self.faces), torch.sigmoid(tile(self.textures))
 
     def set_lr(self, lr_vertices, lr_textures):
-        self.vertices.lr = lr_vertices
-        self.textures.lr = lr_textures
+        """Per-tensor learning-rate factors read by :class:`Adam` (mesh.py:35-37)."""
+        for tensor, factor in ((self.vertices, lr_vertices), (self.textures, lr_textures)):
+            tensor.lr = factor
