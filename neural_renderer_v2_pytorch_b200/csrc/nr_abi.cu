@@ -171,6 +171,12 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(NR_ERR_INVALID_ARGUMENT, "workspace NULL or not 256-byte aligned");
     if (pair_capacity < 0 || pair_capacity > 0x7fffffffLL) return fail(NR_ERR_INVALID_ARGUMENT, "pair_capacity out of range");
     const int tile = tile_edge(cfg);
+    {
+        // work items (warp blocks of all tiles, fill chunks) are counted in 32-bit integers
+        const long long ntx_ = (R + tile - 1) / tile;
+        if ((long long)cfg->batch * ntx_ * ntx_ * 8 > 0x3fffffffLL || (long long)cfg->batch * cfg->num_faces > 0x7fffffffLL)
+            return fail(NR_ERR_INVALID_ARGUMENT, "batch x tiles (or batch x faces) too large for one call: split the batch");
+    }
     const Carve c = carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity, tile);
     if (c.bytes > workspace_bytes) return fail(NR_ERR_WORKSPACE_TOO_SMALL, "workspace smaller than nr_workspace_bytes()");
     if (cfg->batch == 0) return NR_OK;
