@@ -681,9 +681,14 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        ProfScope p(PROF_SETUP, stream);
-        return cudaLaunchKernelEx(&cfg, k_bin_view, a.verts, a.faces, a.nv, a.nf, a.R, a.draw_backside, a.ntx, a.rec,
-                                  a.tile_count, a.pairs, a.pair_capacity, a.hdr, a.tile_list);
+        {
+            ProfScope p(PROF_SETUP, stream);
+            e = cudaLaunchKernelEx(&cfg, k_bin_view, a.verts, a.faces, a.nv, a.nf, a.R, a.draw_backside, a.ntx, a.rec,
+                                   a.tile_count, a.pairs, a.pair_capacity, a.hdr, a.tile_list);
+        }
+        if (e == cudaSuccess) return e;
+        // a device / partition that cannot co-schedule the cluster: nothing ran, take the general path
+        (void)cudaGetLastError();
     }
     // header + tile counts are contiguous in the workspace: one memset
     cudaError_t e;
