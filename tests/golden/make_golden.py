@@ -290,7 +290,24 @@ def make_textured_obj_fixture(nr):
     save("textured_obj_reference_loader", vertices=v, faces=f, vertices_t=vt, faces_t=ft, textures=tex)
 
 
+def make_reference_golden_png_fixture(nr):
+    """The reference's own golden image: tests_torch/data/4e49873292196f02574b5684eaec43e9.png is what
+    tests_torch/test_save_obj.py:43 and tests_chainer/test_rasterize.py:43-72 compare a render of the
+    textured model next to it with (atol 1e-2).  The model is loaded HERE with the reference's
+    load_obj(load_textures=True); the arrays and the golden pixels travel as one fixture."""
+    from PIL import Image
+    import imageio
+    imageio.imread = lambda fn: np.asarray(Image.open(fn).convert("RGB"))
+    base = "/root/reference/tests_torch/data/4e49873292196f02574b5684eaec43e9"
+    v, f, vt, ft, tex = nr.load_obj(base + "/model.obj", load_textures=True)
+    png = np.asarray(Image.open(base + ".png"))
+    save("reference_golden_png_4e4987", vertices=v, faces=f, vertices_t=vt, faces_t=ft,
+         textures=(np.asarray(tex) * 255 + 0.5).astype(np.uint8),      # the atlas is 8-bit image data
+         golden_png=png, viewpoint=nr.get_points_from_angles(2.5, 10, -90))
+
+
 if __name__ == "__main__":
     main()
+    make_reference_golden_png_fixture(import_reference())
     make_textured_obj_fixture(import_reference())
     make_lights_fixture(import_reference())
