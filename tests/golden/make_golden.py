@@ -306,8 +306,15 @@ def make_reference_golden_png_fixture(nr):
          golden_png=png, viewpoint=nr.get_points_from_angles(2.5, 10, -90))
 
 
+def make_gradient_png_fixture():
+    """tests_torch/data/gradient.png, the target silhouette of tests_torch/test_rasterize.py:205-249."""
+    from PIL import Image
+    save("reference_gradient_png", gradient_png=np.asarray(Image.open("/root/reference/tests_torch/data/gradient.png")))
+
+
 if __name__ == "__main__":
     main()
+    make_gradient_png_fixture()
     make_reference_golden_png_fixture(import_reference())
     make_textured_obj_fixture(import_reference())
     make_lights_fixture(import_reference())

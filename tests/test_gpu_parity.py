@@ -719,3 +719,26 @@ def test_square_optimisation_converges(nr):
         if loss.item() < 0.05:
             break
     assert loss.item() < 0.05, "did not converge: %g" % loss.item()
+
+
+def test_reference_backward_case1_with_its_own_target(nr):
+    """tests_torch/test_rasterize.py:205-249 verbatim: the 2-triangle square, target = 1 - gradient.png
+    (the reference's own fixture), 256^2 without anti-aliasing, Adam lr 0.005: the IoU loss must fall
+    below 0.01 within 350 iterations."""
+    dev = "cuda:0"
+    ref_img = np.load(os.path.join(GOLDEN, "reference_gradient_png.npz"))["gradient_png"].astype(np.float32) / 255.
+    target = torch.from_numpy(1 - ref_img[:, :, 0]).to(dev)
+    vertices = torch.nn.Parameter(torch.tensor([[0.1, 0.1, 1.], [-0.1, 0.1, 1.], [-0.1, -0.1, 1.], [0.1, -0.1, 1.]], device=dev))
+    faces = torch.tensor([[0, 1, 2], [0, 2, 3]], dtype=torch.int32, device=dev)
+    opt = torch.optim.Adam([vertices], lr=0.005)
+    iou = None
+    for i in range(350):
+        hp = nr.RasterizeHyperparam(image_size=256, anti_aliasing=False)
+        image = nr.rasterize_silhouettes(vertices[None], faces, nr.RasterizeParam(), hp)[0]
+        iou = 1 - torch.sum(image * target) / torch.sum(image + target - image * target)
+        opt.zero_grad()
+        iou.backward()
+        opt.step()
+        if float(iou.detach()) < 0.01:
+            return
+    raise AssertionError("IoU loss %.4f after 350 iterations" % float(iou.detach()))
