@@ -24,6 +24,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv[1:]:
+    # the CPU arm uses every host core; torchrun exports OMP_NUM_THREADS=1, and the OpenMP runtime reads it
+    # once, when torch loads it
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
