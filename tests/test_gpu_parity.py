@@ -742,3 +742,81 @@ def test_reference_backward_case1_with_its_own_target(nr):
         if float(iou.detach()) < 0.01:
             return
     raise AssertionError("IoU loss %.4f after 350 iterations" % float(iou.detach()))
+
+
+@pytest.mark.parametrize("S,aa,fine", [(64, False, False), (36, True, False), (40, True, True), (50, False, True)])
+def test_kernels_stay_inside_their_buffers(nr, S, aa, fine):
+    """No sanitizer on this pool: every output of the forward / backward is carved out of a larger
+    poisoned allocation and the guard words on both sides must survive (vector and scalar fill paths,
+    16x16 and 8x8 tiles, zero-fill chunks, gradient atomics)."""
+    import ctypes
+    from neural_renderer_v2_pytorch_b200 import _lib, rasterize as rz
+    L = _lib.lib()
+    d = np.load(os.path.join(GOLDEN, "teapot.npz"))
+    B, G_ = 3, 4096
+    g = torch.Generator().manual_seed(S)
+    vw = torch.from_numpy(d["vertices"])[None].repeat(B, 1, 1)
+    eye = nr.get_points_from_angles(torch.full((B,), 2.732), torch.rand(B, generator=g) * 80 - 20, torch.rand(B, generator=g) * 360)
+    v = nr.perspective(nr.look_at(vw, eye)).cuda().contiguous()
+    faces = torch.from_numpy(d["faces"]).cuda()
+    vt_np, ft_np, tex_np = nr.create_textures(faces.shape[0], 2)
+    tex = torch.rand((B,) + tex_np.shape, generator=g).cuda()
+    vt = torch.from_numpy(vt_np)[None].repeat(B, 1, 1).cuda()
+    ft = torch.from_numpy(ft_np).cuda()
+    R = 2 * S if aa else S
+    flags = (_lib.NR_DRAW_RGB | _lib.NR_DRAW_SILHOUETTES | _lib.NR_DRAW_BACKSIDE | (_lib.NR_ANTI_ALIASING if aa else 0) |
+             (_lib.NR_FINE_TILES if fine else 0))
+    cfg = _lib.RasterConfig(batch=B, num_vertices=v.shape[1], num_faces=faces.shape[0], image_size=S, flags=flags,
+                            near_plane=0.1, far_plane=100., eps=1e-5, depth_min_delta=1e-4, num_tex_vertices=vt.shape[1],
+                            tex_height=tex.shape[2], tex_width=tex.shape[3])
+    tile = 8 if fine else 16
+    ntx = (R + tile - 1) // tile
+    cap = 8 * B * faces.shape[0]
+    POISON_I, POISON_F = 0x5a5a5a5a, 12345.5
+
+    def guarded(n, dtype):
+        big = torch.full((n + 2 * G_,), POISON_I if dtype == torch.int32 else POISON_F, dtype=dtype, device="cuda")
+        return big, big[G_:G_ + n]
+
+    def intact(big, n):
+        want = POISON_I if big.dtype == torch.int32 else POISON_F
+        return bool((big[:G_] == want).all()) and bool((big[G_ + n:] == want).all())
+
+    sizes = dict(fim=(B * R * R, torch.int32), images=(B * 4 * S * S, torch.float32), internal=(B * 4 * R * R, torch.float32),
+                 tile_list=(8 + 16 * B * ntx * ntx, torch.int32), gv=(v.numel(), torch.float32), gtex=(tex.numel(), torch.float32),
+                 gvt=(vt.numel(), torch.float32), ws=(int(L.nr_workspace_bytes(ctypes.byref(cfg), cap)) // 4 + 64, torch.int32))
+    buf = {k: guarded(n, dt) for k, (n, dt) in sizes.items()}
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    zf = _lib.ZeroFill(count=3)
+    for i, k in enumerate(("gv", "gtex", "gvt")):
+        zf.ptr[i] = buf[k][1].data_ptr()
+        zf.bytes[i] = buf[k][1].numel() * 4
+    ws = buf["ws"][1]
+    base = (ws.data_ptr() + 255) & ~255
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = L.nr_rasterize_forward(ctypes.byref(cfg), ptr(v), ptr(faces), ptr(vt), ptr(ft), ptr(tex), ptr(buf["fim"][1]), None, None,
+                                ptr(buf["images"][1]), ptr(buf["internal"][1]) if aa else None, ptr(buf["tile_list"][1]),
+                                ctypes.c_void_p(base), ws.numel() * 4 - (base - ws.data_ptr()), cap, None, None,
+                                ctypes.byref(zf), None, stream)
+    _lib.check(rc, "forward")
+    G = torch.randn((B, 4, S, S), generator=g).cuda()
+    saved = buf["internal"][1] if aa else buf["images"][1]
+    rc = L.nr_rasterize_backward(ctypes.byref(cfg), ptr(v), ptr(faces), ptr(vt), ptr(ft), ptr(tex), ptr(buf["fim"][1]), ptr(saved),
+                                 None if fine else ptr(buf["tile_list"][1]), ptr(G), ptr(buf["gv"][1]), ptr(buf["gtex"][1]),
+                                 ptr(buf["gvt"][1]), None, None, stream)
+    _lib.check(rc, "backward")
+    torch.cuda.synchronize()
+    for k, (n, _) in sizes.items():
+        assert intact(buf[k][0], n), "%s: guard words overwritten" % k
+    # and everything inside was written: no poison left in the outputs, gradients finite and non-trivial
+    assert not (buf["fim"][1] == POISON_I).any() and not (buf["images"][1] == POISON_F).any()
+    if aa:
+        assert not (buf["internal"][1] == POISON_F).any()
+    for k in ("gv", "gtex", "gvt"):
+        t = buf[k][1]
+        assert torch.isfinite(t).all() and not (t == POISON_F).any()
+    assert float(buf["gv"][1].abs().sum()) > 0 and float(buf["gtex"][1].abs().sum()) > 0
+    # same numbers as the public API
+    hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=aa)
+    img = nr.rasterize_rgba(v, faces, nr.RasterizeParam(vertices_textures=vt, faces_textures=ft, textures=tex), hp)
+    assert torch.equal(img.reshape(-1), buf["images"][1])
