@@ -744,11 +744,12 @@ def test_reference_backward_case1_with_its_own_target(nr):
     raise AssertionError("IoU loss %.4f after 350 iterations" % float(iou.detach()))
 
 
-@pytest.mark.parametrize("S,aa,fine", [(64, False, False), (36, True, False), (40, True, True), (50, False, True)])
-def test_kernels_stay_inside_their_buffers(nr, S, aa, fine):
+@pytest.mark.parametrize("S,aa,fine,general", [(64, False, False, False), (36, True, False, False), (40, True, True, True),
+                                                (50, False, True, True), (64, True, False, True)])
+def test_kernels_stay_inside_their_buffers(nr, S, aa, fine, general):
     """No sanitizer on this pool: every output of the forward / backward is carved out of a larger
     poisoned allocation and the guard words on both sides must survive (vector and scalar fill paths,
-    16x16 and 8x8 tiles, zero-fill chunks, gradient atomics)."""
+    16x16 and 8x8 tiles, one-kernel and general binning, zero-fill chunks, gradient atomics)."""
     import ctypes
     from neural_renderer_v2_pytorch_b200 import _lib, rasterize as rz
     L = _lib.lib()
@@ -765,7 +766,7 @@ def test_kernels_stay_inside_their_buffers(nr, S, aa, fine):
     ft = torch.from_numpy(ft_np).cuda()
     R = 2 * S if aa else S
     flags = (_lib.NR_DRAW_RGB | _lib.NR_DRAW_SILHOUETTES | _lib.NR_DRAW_BACKSIDE | (_lib.NR_ANTI_ALIASING if aa else 0) |
-             (_lib.NR_FINE_TILES if fine else 0))
+             (_lib.NR_FINE_TILES if fine else 0) | (_lib.NR_GENERAL_BINNING if general else 0))
     cfg = _lib.RasterConfig(batch=B, num_vertices=v.shape[1], num_faces=faces.shape[0], image_size=S, flags=flags,
                             near_plane=0.1, far_plane=100., eps=1e-5, depth_min_delta=1e-4, num_tex_vertices=vt.shape[1],
                             tex_height=tex.shape[2], tex_width=tex.shape[3])
