@@ -286,6 +286,7 @@ k_backward(const BackwardArgs a) {
     // CT = 1 is a lone silhouette or depth channel, CT >= 3 always holds the three colour channels
     const bool rgb = (CT == 1) ? false : ((CT >= 3) ? true : (a.flags & FLAG_RGB) != 0);
     constexpr bool LIT = (CT == 0);      // lights only in the generic variants (keeps the common ones small)
+    const bool has_z = rgb || (a.flags & FLAG_DEPTH) != 0;
     if (fg) {
         if (a.faces) {
             vid[0] = __ldg(a.faces + 3 * (size_t)f);
@@ -397,9 +398,13 @@ k_backward(const BackwardArgs a) {
                     const size_t ok = o + 3 * (size_t)vid[k];
                     float *pf = a.grad_verts + ok;
                     long long *pi = DET ? a.det_verts + ok : nullptr;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        if (vg[3 * k + c] != 0.f) accumulate<DET>(pf, pi, c, vg[3 * k + c], a.det_scale);
+                    // one test per corner instead of one per component (every tested reduction costs a branch
+                    // with a reconvergence barrier); z only moves where there is colour or depth to explain
+                    if ((vg[3 * k] != 0.f) | (vg[3 * k + 1] != 0.f) | (vg[3 * k + 2] != 0.f)) {
+                        accumulate<DET>(pf, pi, 0, vg[3 * k], a.det_scale);
+                        accumulate<DET>(pf, pi, 1, vg[3 * k + 1], a.det_scale);
+                        if (has_z) accumulate<DET>(pf, pi, 2, vg[3 * k + 2], a.det_scale);
+                    }
                 }
             }
         }
@@ -418,7 +423,7 @@ k_backward(const BackwardArgs a) {
                     long long *pi = DET ? a.det_tex + o + tap[t] : nullptr;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (tg[t * 3 + c] != 0.f) accumulate<DET>(pf, pi, c * (int)T, tg[t * 3 + c], a.det_scale);
+                        accumulate<DET>(pf, pi, c * (int)T, tg[t * 3 + c], a.det_scale);
                 }
             }
         }
