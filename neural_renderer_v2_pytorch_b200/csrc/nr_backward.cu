@@ -459,7 +459,8 @@ k_differentiation_backward(const float *__restrict__ images, const float *__rest
 cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     const long long tiles = (long long)a.ntx * a.ntx * a.B;
-    const int grid = (int)(tiles < (long long)a.sm_count * 8 ? tiles : (long long)a.sm_count * 8);
+    // exactly the resident CTAs (4 per SM): a second wave of the static tile stride only adds a tail
+    const int grid = (int)(tiles < (long long)a.sm_count * 4 ? tiles : (long long)a.sm_count * 4);
     dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
     if (a.det_verts) {
