@@ -258,15 +258,37 @@ k_raster(const RasterArgs a) {
         }
     };
 
-    // dynamic scheduling: a warp claims one block at a time; the next claim is issued before the
-    // current block is processed so its latency is hidden
-    constexpr int GRAB = 1;
-    int claim = 0;
-    if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
+    // Scheduling: the CTA claims EIGHT consecutive items (the blocks of one 16x16 tile) with one global
+    // atomicAdd and its warps take them one by one from a shared cursor, so the blocks of a tile run on the
+    // same SM at about the same time (face records and lists shared through L1) and no warp waits for
+    // another except while a batch is being fetched.  One shared word holds both the batch and the number
+    // of items taken from it: s_cur = (first item of the batch / 8) << 5 | taken; the warp that draws
+    // taken == 8 fetches the next batch, later ones (at most 7: 5 bits are plenty) wait for it.
+    constexpr int GRAB = 1, BATCH = 8;
+    __shared__ unsigned s_cur;
+    const int all_items = max(items, fill_items);
+    if (threadIdx.x == 0) s_cur = ((unsigned)atomicAdd(&a.hdr->work_counter, BATCH) >> 3) << 5;
+    __syncthreads();
     while (true) {
-        const int first = __shfl_sync(0xffffffffu, claim, 0);
-        if (first >= max(items, fill_items)) break;
-        if (lane == 0) claim = atomicAdd(&a.hdr->work_counter, GRAB);
+        int first = 0;
+        if (lane == 0) {
+            while (true) {
+                const unsigned v = atomicAdd(&s_cur, 1u);
+                const unsigned taken = v & 31u;
+                if (taken < BATCH) {
+                    first = (int)((v >> 5) << 3) + (int)taken;
+                    break;
+                }
+                if (taken == BATCH) {
+                    const unsigned base = (unsigned)atomicAdd(&a.hdr->work_counter, BATCH);
+                    atomicExch(&s_cur, (base >> 3) << 5);
+                } else {
+                    while ((*reinterpret_cast<volatile unsigned *>(&s_cur) >> 5) == (v >> 5)) { }
+                }
+            }
+        }
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= all_items) break;
         if (first < fill_items) do_fill(first);
     for (int item = first; item < min(first + GRAB, items); ++item) {
         const int4 e0 = tile_entry(tl, item >> BLK_SHIFT);
