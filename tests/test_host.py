@@ -215,3 +215,63 @@ def test_mesh_and_adam_exist_and_work(tmp_path):
     # first step of Adam moves every coordinate by alpha against the sign of its gradient
     assert torch.allclose(p.detach(), torch.tensor([0.9, -1.9]), atol=1e-6)
     assert float(q) == 3.0
+
+
+def test_raster_batch_cursor_protocol():
+    """Model of the lock-free work cursor of k_raster (nr_raster.cu, "Scheduling"): a CTA's 8 warps draw
+    items from one shared word  cur = (batch / 8) << 5 | taken;  the warp that draws taken == 8 fetches
+    the next batch of 8 from the global counter and publishes it with one exchange, later ones wait for
+    the batch field to change.  Under arbitrary interleavings (each shared / global access is one atomic
+    step; a warp may be delayed anywhere in between) every item must be processed exactly once.
+    (A 4-bit `taken` field fails this test: sixteen draws in one epoch carry into the batch field.)"""
+    import random
+
+    def run(seed, total_items, nctas, nwarps=8, taken_bits=5):
+        rnd = random.Random(seed)
+        mask = (1 << taken_bits) - 1
+        counter, done, warps = 0, [], []
+        for _ in range(nctas):
+            cta = {"cur": (counter >> 3) << taken_bits}
+            counter += 8
+            warps += [{"pc": "draw", "cta": cta, "alive": True} for _ in range(nwarps)]
+        for _ in range(10 ** 6):
+            alive = [w for w in warps if w["alive"]]
+            if not alive:
+                break
+            w = rnd.choice(alive)
+            cta = w["cta"]
+            if w["pc"] == "draw":
+                w["v"] = cta["cur"]
+                cta["cur"] += 1
+                w["pc"] = "decode"
+            elif w["pc"] == "decode":
+                taken, batch = w["v"] & mask, w["v"] >> taken_bits
+                if taken < 8:
+                    item = batch * 8 + taken
+                    if item >= total_items:
+                        w["alive"] = False
+                    else:
+                        done.append(item)
+                        w["pc"], w["left"] = "work", rnd.randint(0, 5)
+                else:
+                    w["pc"] = "fetch" if taken == 8 else "wait"
+            elif w["pc"] == "work":
+                w["left"] -= 1
+                if w["left"] <= 0:
+                    w["pc"] = "draw"
+            elif w["pc"] == "fetch":
+                w["base"] = counter
+                counter += 8
+                w["pc"] = "publish"
+            elif w["pc"] == "publish":
+                cta["cur"] = (w["base"] >> 3) << taken_bits
+                w["pc"] = "draw"
+            elif w["pc"] == "wait":
+                if (cta["cur"] >> taken_bits) != (w["v"] >> taken_bits):
+                    w["pc"] = "draw"
+        else:
+            return False
+        return sorted(done) == list(range(total_items))
+
+    assert all(run(seed, total_items=150 + seed, nctas=1 + seed % 4) for seed in range(120))
+    assert not all(run(seed, total_items=150, nctas=2, taken_bits=4) for seed in range(40))
