@@ -4,11 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
 
 One "step" = one forward + backward of ``rasterize_rgba`` over one batch of synthetic views
-(BASELINE.json config 2 at N = 1: teapot, 64 views per GPU, 512x512, no anti-aliasing, RGBA with a
+(BASELINE.json config 2: teapot, a batch of 64 views, 512x512, no anti-aliasing, RGBA with a
 texture_size-4 atlas; upstream gradient G ~ N(0,1) fixed).  Metric:
 megapixel-views per second = views * S^2 / 1e6 / time.  For N > 1 the driver launches this file under
-torchrun; every rank renders its own 64 views (no data-path collective: views are independent), the
-step time is the max over ranks, `value` the aggregate.
+torchrun and config 2's batch of 64 is SHARDED over the ranks (64 / N views per GPU, "scaling":
+"strong", as BASELINE.json configs[1] says; no data-path collective: views are independent); the step
+time is the max over ranks, `value` the aggregate.  ``--scaling weak`` keeps 64 views per GPU instead.
+Config 3 (one shared mesh, 8 views per GPU, gradient all-reduce) is weak-scaled by definition.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline`, `cpu_baseline`,
 `e2e`, `gpu_launches`, `clocks`, `kernels_ms`.
@@ -36,16 +38,20 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (views per GPU, S, anti_aliasing, mode, texture_size)
-    "cfg2": dict(views=64, S=512, aa=False, mode="rgba", ts=4, mesh="teapot"),
-    "cfg2s": dict(views=64, S=512, aa=False, mode="silhouettes", ts=0, mesh="teapot"),
-    "cfg1": dict(views=1, S=256, aa=True, mode="rgba", ts=16, mesh="teapot"),
-    "cfg5": dict(views=32, S=512, aa=True, mode="rgb", ts=4, mesh="teapot"),
+    # views = the batch BASELINE.json names (global batch when strong-scaled, per GPU when weak-scaled)
+    # config 2: the configuration the metric is quoted on; its batch of 64 shards over the GPUs
+    "cfg2": dict(views=64, S=512, aa=False, mode="rgba", ts=4, mesh="teapot", scaling="strong"),
+    "cfg2s": dict(views=64, S=512, aa=False, mode="silhouettes", ts=0, mesh="teapot", scaling="strong"),
+    # config 1: examples_pytorch defaults, one view from (2.732, 30, 40), 256^2 with 2x anti-aliasing, ts 16
+    "cfg1": dict(views=1, S=256, aa=True, mode="rgba", ts=16, mesh="teapot", camera=(2.732, 30., 40.)),
+    # config 5: texture optimisation as examples_pytorch/example3.py: orthographic camera (:40), elevation 0 and
+    # a random azimuth (:53), textures = tanh(parameter) (:54), render_rgb with 2x anti-aliasing
+    "cfg5": dict(views=32, S=512, aa=True, mode="rgb", ts=4, mesh="teapot", ortho=True, tanh=True, elevation0=True),
     # config 2 through the Renderer facade: world-space vertices -> camera transform -> rasterize
-    "cfg2r": dict(views=64, S=512, aa=False, mode="rgba", ts=4, mesh="teapot", renderer=True),
-    # multi-view optimisation of ONE shared 100k-face mesh: gradient all-reduce across ranks
+    "cfg2r": dict(views=64, S=512, aa=False, mode="rgba", ts=4, mesh="teapot", renderer=True, scaling="strong"),
+    # config 3: multi-view optimisation of ONE shared 100k-face mesh, 8 views per GPU: gradient all-reduce
     "cfg3": dict(views=8, S=512, aa=False, mode="silhouettes", ts=0, mesh="sphere", shared=True),
-    # 1M independent ~5 px triangles: stresses binning, list sorting and z-test contention
+    # config 4: 1M independent ~5 px triangles: stresses binning and z-test contention
     "cfg4": dict(views=16, S=1024, aa=False, mode="silhouettes", ts=0, mesh="random1m"),
 }
 METRIC = "megapixel-views/sec fwd+bwd"
@@ -97,12 +103,32 @@ def random_triangle_mesh(nf=1000000, seed=0):
     return v.contiguous(), torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3)
 
 
-def make_inputs(w, seed, device, nr):
-    B, S = w["views"], w["S"]
+def shard_of(w, rank, world, scaling):
+    """(global views, first view, one-past-last view) of `rank`.  Strong scaling: the workload's batch is
+    split over the ranks (balanced, contiguous).  Weak: every rank has the workload's batch."""
+    V = w["views"]
+    if scaling == "strong":
+        base, extra = divmod(V, world)
+        lo = rank * base + min(rank, extra)
+        return V, lo, lo + base + (1 if rank < extra else 0)
+    return V * world, rank * V, (rank + 1) * V
+
+
+def make_inputs(w, seed, device, nr, lo=0, hi=None, total=None):
+    """Synthetic inputs of views [lo, hi) out of a batch of `total` views drawn from one seeded stream
+    (so a sharded run renders exactly the views of the single-GPU run)."""
+    total = w["views"] if total is None else total
+    hi = total if hi is None else hi
+    B, S = hi - lo, w["S"]
     g = torch.Generator().manual_seed(seed)
-    elev = torch.rand(B, generator=g) * 80. - 20.
-    azim = torch.rand(B, generator=g) * 360.
-    eye = nr.get_points_from_angles(torch.full((B,), 2.732), elev, azim)
+    elev = torch.rand(total, generator=g) * 80. - 20.
+    azim = torch.rand(total, generator=g) * 360.
+    dist_ = torch.full((total,), 2.732)
+    if w.get("camera"):
+        dist_, elev, azim = (torch.full((total,), float(x)) for x in w["camera"])
+    if w.get("elevation0"):
+        elev = torch.zeros(total)
+    eye = nr.get_points_from_angles(dist_, elev, azim)[lo:hi]
     mesh = w.get("mesh", "teapot")
     if mesh == "teapot":
         d = np.load(os.path.join(ROOT, "tests", "golden", "teapot.npz"))
@@ -112,21 +138,38 @@ def make_inputs(w, seed, device, nr):
     else:
         v_world, faces = random_triangle_mesh(1000000, seed=0)
     tdev = device if (mesh == "random1m" and str(device) != "cpu") else "cpu"   # 3M vertices x 16 views: transform on the GPU
-    vs = nr.perspective(nr.look_at(v_world.to(tdev)[None].expand(B, -1, -1), eye.to(tdev))).contiguous()
+    vs = nr.look_at(v_world.to(tdev)[None].expand(B, -1, -1), eye.to(tdev))
+    if not w.get("ortho"):
+        vs = nr.perspective(vs)
+    vs = vs.contiguous()
     out = dict(vertices=vs, faces=faces, nv=vs.shape[1], nf=faces.shape[0], T=0, eye=eye, v_world=v_world)
     if w["mode"] in ("rgb", "rgba"):
         vt_np, ft_np, tex_np = nr.create_textures(faces.shape[0], w["ts"])
         gt = torch.Generator().manual_seed(0)
-        out["textures"] = torch.rand((B,) + tex_np.shape, generator=gt)
+        out["textures"] = torch.rand((total,) + tex_np.shape, generator=gt)[lo:hi].contiguous()
         out["vt"] = torch.from_numpy(vt_np)[None].repeat(B, 1, 1).contiguous()
         out["ft"] = torch.from_numpy(ft_np)
         out["T"] = tex_np.shape[1] * tex_np.shape[2]
     C = {"rgba": 4, "rgb": 3, "silhouettes": 1, "depth": 1}[w["mode"]]
     gg = torch.Generator().manual_seed(1)
-    shape = (B, C, S, S) if C > 1 else (B, S, S)
-    out["G"] = torch.randn(shape, generator=gg)
+    shape = (total, C, S, S) if C > 1 else (total, S, S)
+    out["G"] = torch.randn(shape, generator=gg)[lo:hi].contiguous()
     out["C"] = C
     return out
+
+
+def config_of(name, w, inp, world, scaling, local_views, global_views, step_bytes):
+    """The `config` object of the JSON line; both arms build it with this function."""
+    rgb = w["mode"] in ("rgb", "rgba")
+    extras = "".join((", orthographic camera" if w.get("ortho") else "", ", textures = tanh(parameter)" if w.get("tanh") else "",
+                      ", one shared mesh (gradient all-reduced over the ranks)" if w.get("shared") else "",
+                      ", through Renderer.render (fused camera transform)" if w.get("renderer") else ""))
+    return {"workload": "%s: %s (%d v / %d f), batch of %d views, %dx%d, anti_aliasing=%s, %s%s%s"
+                        % (name, w.get("mesh", "teapot"), inp["nv"], inp["nf"], global_views, w["S"], w["S"], w["aa"], w["mode"],
+                           (", texture_size %d (T=%d texels/view)" % (w["ts"], inp["T"])) if rgb else "", extras),
+            "views_per_gpu": local_views, "global_views": global_views, "image_size": w["S"],
+            "parallelism": "dp%d" % world,
+            "l2": "per-GPU per-step working set %.3f GB vs 126 MB L2, no explicit flush" % (step_bytes / 1e9)}
 
 
 class ClockSampler(threading.Thread):
@@ -167,7 +210,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self._stop_evt.is_set():
             self.sample()
-            self._stop_evt.wait(0.01)
+            self._stop_evt.wait(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -187,6 +230,23 @@ def physical_gpu_index(local):
     return local
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, BEFORE any pinned buffer is
+    allocated, so the staging memory of the end-to-end arm lives on the GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 # ------------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import torch.distributed as dist
@@ -199,6 +259,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -207,10 +268,20 @@ def run_ours(args):
         # line; send its log to stderr instead
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    w = WORKLOADS[args.workload]
-    B, S = w["views"], w["S"]
+    w = dict(WORKLOADS[args.workload])
+    if args.views:
+        w["views"] = args.views
+    scaling = args.scaling or w.get("scaling", "weak")
+    S = w["S"]
     R = S * 2 if w["aa"] else S
-    inp = make_inputs(w, seed=1000 + rank, device=dev, nr=nr)
+    V, lo, hi = shard_of(w, rank, world, scaling)
+    B = hi - lo
+    if B <= 0:
+        raise SystemExit("bench.py: %d views cannot be split over %d ranks" % (V, world))
+    if scaling == "strong":
+        inp = make_inputs(w, seed=1000, device=dev, nr=nr, lo=lo, hi=hi, total=V)
+    else:       # every rank draws its own views
+        inp = make_inputs(w, seed=1000 + rank, device=dev, nr=nr)
     C = inp["C"]
     L = _lib.lib()
 
@@ -222,44 +293,51 @@ def run_ours(args):
     fn = {"rgba": nr.rasterize_rgba, "rgb": nr.rasterize_rgb, "silhouettes": nr.rasterize_silhouettes,
           "depth": nr.rasterize_depth}[w["mode"]]
 
-    def step(v, tex):
-        hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"])
-        p = nr.RasterizeParam(vertices_textures=vt, faces_textures=ft, textures=tex) if rgb else nr.RasterizeParam()
-        images = fn(v, faces, p, hp)
-        images.backward(G)           # == ((images * G).sum()).backward(), SURVEY.md 8(d)
-        return images
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident arm: `value`
+    # ---- the differentiable inputs of the step live in ONE flat device buffer (views of it are the
+    # leaves), so the end-to-end arm uploads them with one copy; same for the gradients it reads back
     shared = bool(w.get("shared"))
     if shared:
+        leaves_host = [inp["v_world"][None].contiguous()]
+    elif w.get("renderer"):
+        leaves_host = [inp["v_world"][None].repeat(B, 1, 1).contiguous(), inp["textures"]]
+    else:
+        leaves_host = [inp["vertices"].cpu()] + ([inp["textures"]] if rgb else [])
+    sizes = [t.numel() for t in leaves_host]
+    offs = [sum(sizes[:i]) for i in range(len(sizes))]
+    flat_in = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    params = []
+    for t, o, n in zip(leaves_host, offs, sizes):
+        flat_in[o:o + n].copy_(t.reshape(-1))
+        params.append(flat_in[o:o + n].view(t.shape).requires_grad_(True))
+
+    if shared:
         # ONE mesh parameter for all views of all ranks: world -> screen transform inside the step,
-        # squared-error loss against the unperturbed sphere, gradient summed over views and ranks
-        param = inp["v_world"][None].to(dev).requires_grad_(True)
+        # squared-error loss against the unperturbed sphere (examples_pytorch/example2.py:39-41), gradient
+        # summed over the local views and over the ranks
+        param = params[0]
         eye_d = inp["eye"].to(dev)
         tv, _ = sphere_mesh(225, 0.0)
         with torch.no_grad():
             target = fn(nr.perspective(nr.look_at(tv.to(dev)[None].expand(B, -1, -1), eye_d)), faces,
                         nr.RasterizeParam(), nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"]))
-        params = [param]
         rend = nr.Renderer()
         rend.image_size, rend.anti_aliasing, rend.viewpoints = S, w["aa"], eye_d
 
         def step_fn():
-            # Renderer.render_silhouettes: fused camera transform + rasterizer; the backward sums the
-            # gradient over the local views and all-reduces it over the ranks (parallel.py)
-            images = rend.render_silhouettes(nr.parallel.share_across_views(param, B), faces)
+            # Renderer.render_silhouettes on the shared [1,nv,3] mesh with [B,3] viewpoints: the fused camera
+            # transform projects it into every local view; its backward sums the gradient over the views in
+            # registers, and share_across_ranks all-reduces the [1,nv,3] result over the ranks (parallel.py)
+            images = rend.render_silhouettes(nr.parallel.share_across_ranks(param), faces)
             ((images - target) ** 2).sum().backward()
             return images
     elif w.get("renderer"):
         # the call a user of the reference makes: Renderer.render(world vertices, ...)
-        v_dev = inp["v_world"][None].repeat(B, 1, 1).to(dev).requires_grad_(True)
-        tex_dev = inp["textures"].to(dev).requires_grad_(True)
-        params = [v_dev, tex_dev]
+        v_dev, tex_dev = params
         rend = nr.Renderer()
         rend.image_size, rend.anti_aliasing, rend.viewpoints = S, w["aa"], inp["eye"].to(dev)
         rend.fused_camera = not args.unfused_camera
@@ -269,12 +347,16 @@ def run_ours(args):
             images.backward(G)
             return images
     else:
-        v_dev = inp["vertices"].to(dev).requires_grad_(True)
-        tex_dev = inp["textures"].to(dev).requires_grad_(True) if rgb else None
-        params = [v_dev] + ([tex_dev] if rgb else [])
+        v_dev = params[0]
+        tex_dev = params[1] if rgb else None
 
         def step_fn():
-            return step(v_dev, tex_dev)
+            hp = nr.RasterizeHyperparam(image_size=S, anti_aliasing=w["aa"])
+            tex = torch.tanh(tex_dev) if (rgb and w.get("tanh")) else tex_dev       # example3.py:54
+            p = nr.RasterizeParam(vertices_textures=vt, faces_textures=ft, textures=tex) if rgb else nr.RasterizeParam()
+            images = fn(v_dev, faces, p, hp)
+            images.backward(G)           # == ((images * G).sum()).backward(), SURVEY.md 8(d)
+            return images
 
     def eager_step():
         for p_ in params:
@@ -315,14 +397,14 @@ def run_ours(args):
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     e1.record()
     barrier()
-    clocks = sampler.stop() if sampler else None
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * B * S * S / 1e6 / (ms_step / 1e3)
+    total_views = V if scaling == "strong" else B * world
+    value = total_views * S * S / 1e6 / (ms_step / 1e3)
 
     # ---- per-kernel pass (same inputs, right after the timed region): roofline numbers
     L.nr_profile_enable(1)
@@ -335,35 +417,38 @@ def run_ours(args):
     cnt = (ctypes.c_int32 * _lib.NR_PROF_SLOTS)()
     L.nr_profile_collect(ms, cnt)
     kern = {n: (ms[i] / cnt[i]) for i, n in enumerate(_lib.PROF_SLOT_NAMES) if cnt[i]}
-    if "setup_count" in kern and "scan_tiles" not in kern:
+    if "setup_count" in kern and "scan_tiles" not in kern and "raster_dense" not in kern:
         kern["bin_view"] = kern.pop("setup_count")      # small meshes: the one-kernel cluster binning uses this slot
     # kernels of this library per step (memset nodes not counted)
     launches_per_step = sum(cnt[i] for i, n in enumerate(_lib.PROF_SLOT_NAMES) if n != "memset") / args.steps
 
-    # ---- end-to-end arm: host (pinned) inputs -> H2D -> fwd + bwd -> D2H of the results
-    hosts = [p_.detach().cpu().pin_memory() for p_ in params]
-    gv_host = torch.empty_like(hosts[0]).pin_memory()
-    chk_host = torch.empty(1).pin_memory()
-
-    # Double-buffered pipeline, as a data loader would drive it: while step i runs on the compute
-    # stream, the inputs of step i+1 are uploaded on a copy stream into a staging set; a device-to-
-    # device copy moves them into the (static) inputs of the captured step.  Every step uploads its
-    # own inputs and reads its results back; all of it is inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
+    # ---- end-to-end arm: host (pinned) inputs -> H2D -> fwd + bwd -> D2H of every gradient
+    # Double-buffered pipeline, as a data loader would drive it: while step i runs on the compute stream,
+    # the inputs of step i+1 are uploaded on a copy stream (ONE cudaMemcpyAsync from one pinned buffer into
+    # a staging buffer; a device-to-device copy moves them into the static inputs of the captured step)
+    # and the gradients of step i-1 go back on a third stream (ONE cudaMemcpyAsync into pinned memory).
+    # Every step uploads its own inputs and reads all of its gradients back; all inside the timed region.
+    host_in = torch.empty(flat_in.numel(), dtype=torch.float32).pin_memory()
+    host_in.copy_(flat_in.cpu())
+    n_out = flat_in.numel() + 1                           # every gradient + a checksum of the images
+    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
+    up_stream, down_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     compute_stream = torch.cuda.current_stream(dev)
-    stages = [[torch.empty_like(p_.data) for p_ in params] for _ in range(2)]
+    stage_in = [torch.empty_like(flat_in) for _ in range(2)]
+    stage_out = [torch.empty(n_out, dtype=torch.float32, device=dev) for _ in range(2)]
     ev_up = [torch.cuda.Event() for _ in range(2)]       # staging set filled
     ev_free = [torch.cuda.Event() for _ in range(2)]     # staging set consumed
+    ev_grad = [torch.cuda.Event() for _ in range(2)]     # gradients of the slot gathered
+    ev_down = [torch.cuda.Event() for _ in range(2)]     # ... and copied to the host
 
     def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[slot])
-            for s_, h_ in zip(stages[slot], hosts):
-                s_.copy_(h_, non_blocking=True)
-            ev_up[slot].record(copy_stream)
+        with torch.cuda.stream(up_stream):
+            up_stream.wait_event(ev_free[slot])
+            stage_in[slot].copy_(host_in, non_blocking=True)
+            ev_up[slot].record(up_stream)
 
-    def e2e_run(n):
-        for ev in ev_free:
+    def e2e_run(n, h2d_only=False):
+        for ev in ev_free + ev_down:
             ev.record(compute_stream)
         upload(0)
         for i in range(n):
@@ -371,27 +456,46 @@ def run_ours(args):
             if i + 1 < n:
                 upload(slot ^ 1)
             compute_stream.wait_event(ev_up[slot])
-            for p_, s_ in zip(params, stages[slot]):
-                p_.data.copy_(s_, non_blocking=True)
+            with torch.no_grad():
+                flat_in.copy_(stage_in[slot], non_blocking=True)
             ev_free[slot].record(compute_stream)
+            if h2d_only:
+                continue
             images = run_step()
-            gv_host.copy_(params[0].grad, non_blocking=True)
-            chk_host.copy_(images.sum().reshape(1), non_blocking=True)
+            compute_stream.wait_event(ev_down[slot])      # the slot's previous read-back has left the device
+            with torch.no_grad():
+                for p_, o, nn_ in zip(params, offs, sizes):
+                    stage_out[slot][o:o + nn_].copy_(p_.grad.reshape(-1), non_blocking=True)
+                stage_out[slot][-1:].copy_(images.sum().reshape(1), non_blocking=True)
+            ev_grad[slot].record(compute_stream)
+            with torch.cuda.stream(down_stream):
+                down_stream.wait_event(ev_grad[slot])
+                host_out[slot].copy_(stage_out[slot], non_blocking=True)
+                ev_down[slot].record(down_stream)
+        compute_stream.wait_stream(down_stream)
+        compute_stream.wait_stream(up_stream)
+
+    def timed(fn_, n):
+        barrier()
+        e0.record()
+        fn_(n)
+        e1.record()
+        barrier()
+        t_ = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([t_], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ = float(tt.item())
+        return t_ / n
 
     e2e_run(max(args.warmup, 4))
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e_value = world * B * S * S / 1e6 / (ms_e2e / args.steps / 1e3)
-    h2d = sum(h_.numel() * 4 for h_ in hosts)
-    d2h = gv_host.numel() * 4 + 4
+    ms_e2e = timed(e2e_run, args.steps)
+    ms_h2d = timed(lambda n: e2e_run(n, h2d_only=True), args.steps)      # the upload alone, for the scaling diagnosis
+    clocks = sampler.stop() if sampler else None
+    e2e_value = total_views * S * S / 1e6 / (ms_e2e / 1e3)
+    h2d = host_in.numel() * 4
+    d2h = n_out * 4
+    grad_ok = bool(torch.isfinite(host_out[(args.steps - 1) & 1]).all())
 
     def finish():
         """Leave without tearing NCCL down: destroy_process_group() can block for minutes on a communicator
@@ -410,20 +514,23 @@ def run_ours(args):
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     fwd_b, bwd_b = algorithmic_bytes(inp["nv"], inp["nf"], inp["T"], R * R, C, S)
-    shares = {"raster": fwd_b * B, "backward": bwd_b * B}
+    shares = {"raster": fwd_b * B, "raster_dense": fwd_b * B, "backward": bwd_b * B}
     dom = max((k for k in kern if k in shares), key=lambda k: kern[k])
     achieved = shares[dom] / (kern[dom] / 1e3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(args.workload, {}).get(dom)
+                tj = json.load(f)
+            traffic = tj.get(args.workload, {}).get(dom) if B == WORKLOADS[args.workload]["views"] else None
+            traffic_src = tj.get("_source")
         except Exception:
             traffic = None
     step_bytes = (fwd_b + bwd_b) * B
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": shares[dom], "kernel_ms": round(kern[dom], 4),
                 "peak_source": peak_src,
                 "step_frac": round(step_bytes / (ms_step / 1e3) / 1e9 / peak, 4),
@@ -435,16 +542,15 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s (%d v / %d f), %d views per GPU, %dx%d, anti_aliasing=%s, %s%s"
-                               % (args.workload, w.get("mesh", "teapot"), inp["nv"], inp["nf"], B, S, S, w["aa"], w["mode"],
-                                  (", texture_size %d (T=%d texels/view)" % (w["ts"], inp["T"])) if rgb else ""),
-                   "views_per_gpu": B, "global_views": B * world, "image_size": S, "parallelism": "dp%d" % world,
-                   "l2": "per-step working set %.2f GB > 126 MB L2, no explicit flush" % (step_bytes / 1e9)},
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(args.workload, w, inp, world, scaling, B, total_views, step_bytes),
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(ms_e2e / args.steps, 4),
-                "pipeline": "inputs of step i+1 uploaded from pinned memory on a copy stream while step i runs; "
-                            "per step: H2D of all differentiable inputs, fwd+bwd, D2H of vertex gradients + checksum"},
+                "ms_per_step": round(ms_e2e, 4), "h2d_only_ms_per_step": round(ms_h2d, 4),
+                "host_cpus_bound": numa_cpus, "gradients_finite": grad_ok,
+                "pipeline": "per step: ONE pinned H2D copy of every differentiable input (uploaded on a copy stream "
+                            "while the previous step runs), fwd+bwd, ONE D2H copy of EVERY gradient the step produces "
+                            "+ an image checksum on a third stream; the images themselves stay on the device, as in "
+                            "an optimisation loop whose loss is evaluated there"},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "launch_mode": "cuda graph replay of the whole step" if use_graph else "eager (python)",
         "host_ms_per_step": round(host_ms, 4),
@@ -460,19 +566,23 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------- CPU side
 def oracle_step(inp, w, views):
-    """One fwd + bwd of the CPU oracle (C z-buffer / weight map with OpenMP + torch-CPU stages)."""
+    """One fwd + bwd of the CPU oracle (C z-buffer / weight map with OpenMP + torch-CPU stages).
+    Returns (images, leaves): the leaves carry the gradients."""
     from oracle import pipeline as ref
-    v = inp["vertices"][:views].clone().requires_grad_(True)
+    v = inp["vertices"][:views].cpu().clone().requires_grad_(True)
     kw = {}
+    leaves = [v]
     rgb = w["mode"] in ("rgb", "rgba")
     if rgb:
         tex = inp["textures"][:views].clone().requires_grad_(True)
-        kw = dict(vertices_textures=inp["vt"][:views], faces_textures=inp["ft"].numpy(), textures=tex)
+        leaves.append(tex)
+        kw = dict(vertices_textures=inp["vt"][:views], faces_textures=inp["ft"].numpy(),
+                  textures=torch.tanh(tex) if w.get("tanh") else tex)
     img = ref.rasterize(v, inp["faces"], w["S"], w["aa"], draw_rgb=rgb,
                         draw_silhouettes=w["mode"] in ("silhouettes", "rgba"), draw_depth=w["mode"] == "depth", **kw)
     G = inp["G"][:views]
     img.backward(G if G.ndim == 4 else G[:, None])
-    return img
+    return img, leaves
 
 
 def cpu_cores():
@@ -511,21 +621,26 @@ def cpu_baseline_sample(workload, budget_s=12.0):
 def run_reference(args):
     """--impl reference: the oracle port of the reference's path on the host cores.
     (oracle/_ref holds the reference's CUDA kernels, which need a GPU; the reference ships no CPU
-    implementation of the z-buffer, so the CPU arm is kind = "port".)"""
+    implementation of the z-buffer, so the CPU arm is kind = "port".)  Every step renders the WHOLE batch
+    of the workload (all 64 views of config 2) as long as the run stays within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import neural_renderer_v2_pytorch_b200 as nr
-    w = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = dict(WORKLOADS[args.workload])
+    if args.views:
+        w["views"] = args.views
+    scaling = args.scaling or w.get("scaling", "weak")
     cores = cpu_cores()
     torch.set_num_threads(cores)
     inp = make_inputs(w, seed=1000, device="cpu", nr=nr)
     oracle_step(inp, w, 1)
     t0 = time.perf_counter()
-    oracle_step(inp, w, 1)
-    t1 = time.perf_counter() - t0
+    oracle_step(inp, w, min(4, w["views"]))
+    t1 = (time.perf_counter() - t0) / min(4, w["views"])
     total_steps = args.steps + max(args.warmup, 1)
-    views = int(max(1, min(w["views"], 150.0 / (t1 * total_steps))))
+    views = int(max(1, min(w["views"], 280.0 / (t1 * total_steps))))
     for _ in range(max(args.warmup, 1)):
         oracle_step(inp, w, views)
     t0 = time.perf_counter()
@@ -533,14 +648,19 @@ def run_reference(args):
         oracle_step(inp, w, views)
     t = time.perf_counter() - t0
     value = views * w["S"] ** 2 * args.steps / 1e6 / t
-    sample = ("each step = %d of %d views of %s (fwd+bwd); C z-buffer/weight-map restatement (OpenMP) + "
-              "torch-CPU stages" % (views, w["views"], args.workload))
+    S = w["S"]
+    R = S * 2 if w["aa"] else S
+    fwd_b, bwd_b = algorithmic_bytes(inp["nv"], inp["nf"], inp["T"], R * R, inp["C"], S)
+    V = w["views"] if scaling == "strong" else w["views"] * world
+    local = (w["views"] + world - 1) // world if scaling == "strong" else w["views"]
+    sample = ("each step = %s views of %s (fwd+bwd) on the host; C z-buffer/weight-map restatement (OpenMP) + "
+              "torch-CPU stages" % ("all %d" % views if views == w["views"] else "%d of the %d" % (views, w["views"]),
+                                     args.workload))
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT,
-            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 1),
-            "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: teapot, %dx%d, anti_aliasing=%s, %s; bounded sample of %d views per step"
-                                   % (args.workload, w["S"], w["S"], w["aa"], w["mode"], views)},
+            "config": config_of(args.workload, w, inp, world, scaling, local, V, (fwd_b + bwd_b) * local),
             "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -553,6 +673,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="strong: the workload's batch is sharded over the GPUs (default for config 2); "
+                         "weak: every GPU renders the workload's batch (default for the others)")
+    ap.add_argument("--views", type=int, default=0, help="override the workload's batch (single-GPU studies of the sharded sizes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused-camera", action="store_true", help="cfg2r: camera transform as torch ops")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 2
+#define NR_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NR_API __attribute__((visibility("default")))
@@ -65,6 +65,11 @@ enum {
                                  tile_list is then in 8x8 units, [8 + 16 * B * ceil(R/8)^2] ints, and must NOT
                                  be passed to nr_rasterize_backward (pass NULL); NR_SPARSE_MAPS is ignored. */
 #define NR_GENERAL_BINNING 64 /* forward: never take the one-kernel small-mesh binning path (see nrBinStats) */
+#define NR_DENSE_RASTER 512   /* forward: meshes of SMALL triangles (nrBinStats.total_pairs of an earlier call >= ~32 per
+                                 tile on average, a few tiles per face): general binning WITHOUT the per-tile sort, and
+                                 the face-parallel raster kernel (one CTA per 16x16 tile, one thread per face, z-buffer
+                                 in shared memory, exact resolution of contested pixels: nr_raster_dense.cu).  Same
+                                 results bit for bit; implies NR_GENERAL_BINNING, excludes NR_FINE_TILES. */
 
 /* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */
 typedef struct nrRasterConfig {
@@ -131,7 +136,9 @@ typedef struct nrBinStats {
     int32_t overflow;         /* 1: pair list longer than pair_capacity; 2: a view has more pairs than the
                                  one-kernel small-mesh binning holds in shared memory -> pass
                                  NR_GENERAL_BINNING from now on.  Results are correct either way. */
-    int32_t bad_index;        /* 1: a face referenced a vertex outside [0, nv) (face dropped) */
+    int32_t bad_index;        /* bit 0: a face referenced a vertex outside [0, nv) (face dropped);
+                                 bit 1: a face referenced a texture vertex outside [0, nvt) (its pixels are black,
+                                 no gradient).  Both are an IndexError in the reference (rasterize.py:232,246). */
 } nrBinStats;
 
 NR_API int nr_abi_version(void);
@@ -151,9 +158,10 @@ NR_API int nr_event_query(void *event); /* 1 complete, 0 not yet, -1 error */
  * bracketed by CUDA events on its launch stream.  nr_profile_collect synchronises those events and
  * ADDS the elapsed milliseconds / launch counts per slot into ms[NR_PROF_SLOTS] / launches[...]
  * (slots: 0 memset, 1 setup_count, 2 scan_tiles, 3 scatter, 4 sort_long, 5 raster, 6 backward,
- * 7 differentiation_backward, 8 weight_map_compat), then forgets them.
+ * 7 differentiation_backward, 8 weight_map_compat, 9 raster_dense, 10 camera_forward, 11 camera_backward),
+ * then forgets them.
  */
-#define NR_PROF_SLOTS 9
+#define NR_PROF_SLOTS 12
 NR_API int nr_profile_enable(int on);
 NR_API int nr_profile_collect(float *ms, int32_t *launches);
 
@@ -190,8 +198,7 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   workspace           nr_workspace_bytes(cfg, pair_capacity) bytes, 256-byte aligned
  *   stats_host          optional pinned host nrBinStats
  *   stats_event         optional cudaEvent_t (as void*, e.g. from nr_event_create) recorded right
- *                       after the stats copy, i.e. BEFORE the raster kernel: waiting on it costs
- *                       the binning kernels only
+ *                       after the stats copy, which follows the raster kernel (bad_index bit 1 is set there)
  *   zero_fill           optional, see nrZeroFill
  *
  * Every element of face_index_map / images / images_internal is written (empty tiles and background
@@ -223,7 +230,7 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
  *                       zero-filled bytes.  Contributions are then rounded once to 64-bit fixed point
  *                       (x 2^32) and summed with integer atomics, so the gradients are bit-identical from
  *                       run to run (float atomics depend on arrival order).  Valid while every |sum| < 2.1e9;
- *                       absolute resolution 2.3e-10.
+ *                       absolute resolution 2.3e-10.  Covers grad_vertex_normals (lights) as well.
  */
 NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
@@ -246,22 +253,31 @@ NR_API int nr_differentiation_backward(const float *images, const float *grad_ou
  * Fused camera transform (look_at.py:28-42 + perspective.py:9-17): out = persp(R (v - eye)).
  *   vertices [B, nv, 3] world space, rotation [B, 3, 3] (rows = camera x, y, z axes), eye [B, 3]
  *   out [B, nv, 3] screen space; perspective != 0 divides x and y by z and by width = tan(angle).
- * Backward: grad_vertices [B, nv, 3] is written; partial [B, nr_camera_partial_blocks(nv), 12] receives
- * per-block sums of d loss / d rotation (9, row-major) and d loss / d eye (3) - sum them over dim 1.
+ *   shared_mesh != 0: `vertices` is ONE mesh [1, nv, 3] seen by all B cameras (the reference gets the same by
+ *   broadcasting, look_at.py:41; multi-view optimisation, examples_pytorch/example2.py).
+ * Backward: grad_vertices [B, nv, 3] is written - with shared_mesh [1, nv, 3], the sum over the B views in
+ * view order (deterministic; no [B, nv, 3] intermediate, no separate reduction); partial
+ * [B, nr_camera_partial_blocks(nv), 12] receives per-block sums of d loss / d rotation (9, row-major) and
+ * d loss / d eye (3) - sum them over dim 1 - or is NULL when the cameras need no gradient.
  */
 NR_API int nr_camera_partial_blocks(int32_t num_vertices);
 NR_API int nr_camera_forward(const float *vertices, const float *rotation, const float *eye, float *out,
                              int32_t batch, int32_t num_vertices, int32_t perspective, float width,
-                             void *stream);
+                             int32_t shared_mesh, void *stream);
 NR_API int nr_camera_backward(const float *vertices, const float *rotation, const float *eye,
                               const float *grad_out, float *grad_vertices, float *partial, int32_t batch,
-                              int32_t num_vertices, int32_t perspective, float width, void *stream);
+                              int32_t num_vertices, int32_t perspective, float width, int32_t shared_mesh,
+                              void *stream);
 
 /*
  * Same operator as face_index_map_forward_safe (rasterize_cuda.cpp:55-65):
  *   faces [B, nf, 3, 3], face_index [B*S*S] written in place (pre-fill not required).
- * `eps` is accepted and unused, like in the reference kernel.  Scratch is taken from a
- * per-device cache owned by the library (this call synchronises once on the bin statistics).
+ * `eps` is accepted and unused, like in the reference kernel.  Like the reference operator the call is
+ * ASYNCHRONOUS: it enqueues on `stream` and returns.  Scratch comes from a per (device, stream) cache owned by
+ * the library, sized from the statistics of the previous calls on that stream (read when their event has
+ * completed, never waited for); a call whose pair list outgrows the scratch is still exact (device-side
+ * fallback, see nrBinStats) and the next one gets a larger scratch.  The only host synchronisation is a
+ * cudaStreamSynchronize(stream) in front of a scratch REallocation (growth), i.e. in the first call(s) of a shape.
  */
 NR_API int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int32_t batch,
                                    int32_t num_faces, int32_t image_size, float near_plane,

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libnr_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NR_OK = 0
 NR_ERR_INVALID_ARGUMENT = 1
 NR_ERR_CUDA = 2
@@ -26,6 +26,7 @@ NR_DETERMINISTIC = 32
 NR_GENERAL_BINNING = 64
 NR_SPARSE_MAPS = 128
 NR_FINE_TILES = 256
+NR_DENSE_RASTER = 512
 
 # every symbol include/nr_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (
@@ -35,9 +36,10 @@ SYMBOLS = (
     "nr_profile_enable", "nr_profile_collect", "nr_camera_partial_blocks", "nr_camera_forward",
     "nr_camera_backward",
 )
-NR_PROF_SLOTS = 9
+NR_PROF_SLOTS = 12
 PROF_SLOT_NAMES = ("memset", "setup_count", "scan_tiles", "scatter", "sort_long", "raster", "backward",
-                   "differentiation_backward", "weight_map_compat")
+                   "differentiation_backward", "weight_map_compat", "raster_dense", "camera_forward",
+                   "camera_backward")
 
 
 class RasterConfig(ctypes.Structure):
@@ -137,9 +139,9 @@ def lib():
     L.nr_camera_partial_blocks.restype = ctypes.c_int
     L.nr_camera_partial_blocks.argtypes = [i32]
     L.nr_camera_forward.restype = ctypes.c_int
-    L.nr_camera_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    L.nr_camera_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     L.nr_camera_backward.restype = ctypes.c_int
-    L.nr_camera_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    L.nr_camera_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     if L.nr_abi_version() != ABI_VERSION:
         raise RuntimeError("libnr_b200.so ABI version mismatch")
     _lib = L

@@ -19,47 +19,69 @@ from .perspective import _PI_REF
 
 
 class _CameraTransform(torch.autograd.Function):
+    """vertices [B,nv,3], or ONE mesh [1,nv,3] seen by all B cameras (``rotation`` [B,3,3], ``eye`` [B,3]):
+    the kernels broadcast it, and the backward sums its gradient over the views in registers, view by view
+    (deterministic, no [B,nv,3] intermediate and no separate reduction)."""
+
     @staticmethod
     def forward(ctx, vertices, rotation, eye, perspective, width):
         v = vertices.detach().to(torch.float32).contiguous()
         r = rotation.detach().to(torch.float32).contiguous()
         e = eye.detach().to(torch.float32).contiguous()
-        B, nv = v.shape[:2]
-        out = torch.empty_like(v)
+        B, nv = r.shape[0], v.shape[1]
+        shared = int(v.shape[0] == 1 and B > 1)
+        out = torch.empty((B, nv, 3), dtype=torch.float32, device=v.device)
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream(v.device).cuda_stream
             rc = _lib.lib().nr_camera_forward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
                                               ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, nv,
-                                              int(perspective), float(width), ctypes.c_void_p(stream))
+                                              int(perspective), float(width), shared, ctypes.c_void_p(stream))
         _lib.check(rc, "nr_camera_forward")
         ctx.save_for_backward(v, r, e)
-        ctx.perspective, ctx.width = int(perspective), float(width)
+        ctx.perspective, ctx.width, ctx.shared = int(perspective), float(width), shared
+        ctx.in_dtype = vertices.dtype
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         v, r, e = ctx.saved_tensors
         g = grad_out.detach().to(torch.float32).contiguous()
-        B, nv = v.shape[:2]
+        B, nv = r.shape[0], v.shape[1]
         L = _lib.lib()
         gv = torch.empty_like(v)
-        partial = torch.empty((B, L.nr_camera_partial_blocks(nv), 12), dtype=torch.float32, device=v.device)
+        need_cam = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        partial = None
+        if need_cam:
+            partial = torch.empty((B, L.nr_camera_partial_blocks(nv), 12), dtype=torch.float32, device=v.device)
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream(v.device).cuda_stream
             rc = L.nr_camera_backward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
                                       ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(g.data_ptr()),
-                                      ctypes.c_void_p(gv.data_ptr()), ctypes.c_void_p(partial.data_ptr()), B, nv,
-                                      ctx.perspective, ctx.width, ctypes.c_void_p(stream))
+                                      ctypes.c_void_p(gv.data_ptr()),
+                                      ctypes.c_void_p(partial.data_ptr()) if partial is not None else None, B, nv,
+                                      ctx.perspective, ctx.width, ctx.shared, ctypes.c_void_p(stream))
         _lib.check(rc, "nr_camera_backward")
+        if gv.dtype != ctx.in_dtype:
+            gv = gv.to(ctx.in_dtype)
+        if not need_cam:
+            return gv, None, None, None, None
         red = partial.sum(1)                               # fixed-order reduction of the per-block sums
         return gv, red[:, :9].reshape(B, 3, 3), red[:, 9:], None, None
 
 
 def transform_vertices(vertices, viewpoints, camera_mode="look_at", camera_direction=None, perspective=True,
                        viewing_angle=30., at=None, up=None):
-    """Screen-space vertices [B,nv,3] of ``vertices`` [B,nv,3] (CUDA) seen from ``viewpoints``."""
+    """Screen-space vertices [B,nv,3] of ``vertices`` [B,nv,3] (CUDA) seen from ``viewpoints``.
+
+    ``vertices`` may also be ONE mesh [1,nv,3] with ``viewpoints`` [B,3] (multi-view optimisation of a shared mesh,
+    examples_pytorch/example2.py): it is projected into every view, and its gradient is the sum over the views."""
     assert vertices.ndim == 3
     dev, B = vertices.device, vertices.shape[0]
+    if B == 1:
+        for t in (viewpoints, camera_direction if camera_mode == "look" else None, at, up):
+            if torch.is_tensor(t) and t.ndim == 2 and t.shape[0] > 1:
+                B = t.shape[0]
+                break
     eye = _as_batch(viewpoints, None, B, dev)
     up = _as_batch(up, [0., 1., 0.], B, dev)
     if camera_mode == "look_at":

@@ -71,7 +71,9 @@ int sm_count_cached() {
 }
 
 // tile edge of the binning: 16, or 8 with NR_FINE_TILES (which implies the general binning path)
-int tile_edge(const nrRasterConfig *cfg) { return (cfg->flags & NR_FINE_TILES) ? nr::FINE_TILE : nr::TILE; }
+int tile_edge(const nrRasterConfig *cfg) {
+    return ((cfg->flags & NR_FINE_TILES) && !(cfg->flags & NR_DENSE_RASTER)) ? nr::FINE_TILE : nr::TILE;
+}
 
 int check_config(const nrRasterConfig *cfg) {
     if (!cfg) return fail(NR_ERR_INVALID_ARGUMENT, "config is NULL");
@@ -85,16 +87,25 @@ int check_config(const nrRasterConfig *cfg) {
     return NR_OK;
 }
 
-// per-device scratch for the two reference-signature operators
+// scratch of the reference-signature operator, one per (device, stream): the operator is asynchronous, so two
+// streams must not share a workspace
 struct CompatScratch {
+    int device = -1;
+    cudaStream_t stream = nullptr;
     void *ptr = nullptr;
     size_t bytes = 0;
     long long pair_capacity = 0;
-    nrBinStats *stats_host = nullptr;
+    nrBinStats *stats_host = nullptr;    // pinned; written by the copy that follows the raster kernel
+    cudaEvent_t stats_event = nullptr;
+    bool pending = false;                // a call whose statistics have not been read yet
+    int pend_faces = 0, pend_size = 0;   // its shape
     int general_faces = -1, general_size = -1;   // this shape outgrew the one-kernel binning (nrBinStats.overflow == 2)
+    unsigned long long last_use = 0;
 };
 std::mutex g_compat_mu;
-CompatScratch g_compat[64];
+constexpr int COMPAT_SLOTS = 32;
+CompatScratch g_compat[COMPAT_SLOTS];
+unsigned long long g_compat_clock = 0;
 
 }  // namespace
 
@@ -137,9 +148,11 @@ int nr_event_synchronize(void *event) {
 
 size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg) {
     if (!cfg) return 0;
+    // vertices, textures, vertices_textures, vertex normals (lights), back to back
     const size_t n = (size_t)cfg->batch * cfg->num_vertices * 3 +
                      (size_t)cfg->batch * 3 * cfg->tex_height * cfg->tex_width +
-                     (size_t)cfg->batch * cfg->num_tex_vertices * 2;
+                     (size_t)cfg->batch * cfg->num_tex_vertices * 2 +
+                     (size_t)cfg->batch * cfg->num_vertices * 3;
     return n * sizeof(long long);
 }
 
@@ -200,7 +213,9 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.hdr = c.hdr;
     ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
-    ba.one_cta_per_view = (cfg->flags & (NR_GENERAL_BINNING | NR_FINE_TILES)) ? 0 : 1;
+    const bool dense = (cfg->flags & NR_DENSE_RASTER) != 0;
+    ba.one_cta_per_view = (cfg->flags & (NR_GENERAL_BINNING | NR_FINE_TILES | NR_DENSE_RASTER)) ? 0 : 1;
+    ba.unsorted = dense ? 1 : 0;
 
     nr::RasterArgs ra;
     ra.rec = c.rec;
@@ -261,6 +276,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     if ((e = nr::launch_background_fill(ra, stream)) != cudaSuccess) return fail_cuda(e, "map fill");
     e = nr::launch_binning(ba, stream);
     if (e != cudaSuccess) return fail_cuda(e, "binning");
+    e = dense ? nr::launch_raster_dense(ra, stream) : nr::launch_raster(ra, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "raster");
     if (stats_host) {
         e = cudaMemcpyAsync(stats_host, c.hdr, sizeof(nrBinStats), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return fail_cuda(e, "stats copy");
@@ -269,8 +286,6 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
         e = cudaEventRecord((cudaEvent_t)stats_event, stream);
         if (e != cudaSuccess) return fail_cuda(e, "stats event");
     }
-    e = nr::launch_raster(ra, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "raster");
     return NR_OK;
 }
 
@@ -309,7 +324,7 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
         a.lights = nr::LightArgs{lights->num_lights, lights->types, lights->data, lights->vertex_normals,
                                  lights->grad_vertex_normals, nullptr};
     }
-    a.det_verts = a.det_tex = a.det_vt = nullptr;
+    a.det_verts = a.det_tex = a.det_vt = a.det_vn = nullptr;
     a.det_scale = 4294967296.f;     // 2^32: resolution 2.3e-10, |sum| < 2.1e9
     if (cfg->flags & NR_DETERMINISTIC) {
         if (!deterministic_scratch || ((uintptr_t)deterministic_scratch & 7))
@@ -321,7 +336,11 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
             a.det_tex = p;
             p += (size_t)cfg->batch * 3 * cfg->tex_height * cfg->tex_width;
         }
-        if (grad_vertices_textures) a.det_vt = p;
+        if (grad_vertices_textures) {
+            a.det_vt = p;
+            p += (size_t)cfg->batch * cfg->num_tex_vertices * 2;
+        }
+        if (a.lights.grad_vnormals) a.det_vn = p;
     }
     a.B = cfg->batch;
     a.nv = cfg->num_vertices;
@@ -375,41 +394,81 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
 
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return fail(NR_ERR_INVALID_ARGUMENT, "device ordinal >= 64");
     std::lock_guard<std::mutex> lock(g_compat_mu);
-    CompatScratch &s = g_compat[dev];
+    // the scratch of this (device, stream); the least recently used slot is recycled when all are taken
+    CompatScratch *sp = nullptr, *lru = &g_compat[0];
+    for (CompatScratch &c : g_compat) {
+        if (c.device == dev && c.stream == stream) { sp = &c; break; }
+        if (c.last_use < lru->last_use) lru = &c;
+    }
+    if (!sp) {
+        sp = lru;
+        if (sp->device >= 0) {               // recycle: its work must have left the GPU before the memory goes
+            int cur = dev;
+            cudaSetDevice(sp->device);
+            cudaStreamSynchronize(sp->stream);
+            if (sp->ptr) cudaFree(sp->ptr);
+            if (sp->stats_host) cudaFreeHost(sp->stats_host);
+            if (sp->stats_event) cudaEventDestroy(sp->stats_event);
+            cudaSetDevice(cur);
+            (void)cudaGetLastError();
+        }
+        *sp = CompatScratch();
+        sp->device = dev;
+        sp->stream = stream;
+    }
+    CompatScratch &s = *sp;
+    s.last_use = ++g_compat_clock;
     if (!s.stats_host) {
         cudaError_t e = cudaMallocHost((void **)&s.stats_host, sizeof(nrBinStats));
         if (e != cudaSuccess) return fail_cuda(e, "cudaMallocHost");
+        memset(s.stats_host, 0, sizeof(nrBinStats));
+        e = cudaEventCreateWithFlags(&s.stats_event, cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaEventCreate");
     }
-    long long cap = s.pair_capacity > 0 ? s.pair_capacity : (long long)batch * num_faces * 4 + 1024;
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        const size_t need = nr_workspace_bytes(&cfg, cap);
-        if (need > s.bytes) {
-            cudaStreamSynchronize(stream);
-            if (s.ptr) cudaFree(s.ptr);
-            s.ptr = nullptr;
-            s.bytes = 0;
-            cudaError_t e = cudaMalloc(&s.ptr, need);
-            if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)");
-            s.bytes = need;
+    // statistics of the previous call on this stream, if they have arrived (never waited for)
+    if (s.pending && cudaEventQuery(s.stats_event) == cudaSuccess) {
+        s.pending = false;
+        if (s.stats_host->overflow) {
+            const long long want = (long long)s.stats_host->total_pairs + (s.stats_host->total_pairs >> 2) + 1024;
+            if (want > s.pair_capacity) s.pair_capacity = want;
+            if (s.stats_host->overflow == 2) {
+                s.general_faces = s.pend_faces;
+                s.general_size = s.pend_size;
+            }
         }
-        s.pair_capacity = cap;
-        if (s.general_faces == num_faces && s.general_size == image_size) cfg.flags |= NR_GENERAL_BINNING;
-        int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr,
-                                      nullptr, nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, s.stats_host, nullptr, nullptr,
-                                      nullptr, stream);
-        if (rc != NR_OK) return rc;
+    }
+    (void)cudaGetLastError();        // cudaErrorNotReady of the query is not an error
+    long long cap = (long long)batch * num_faces * 4 + 1024;
+    if (s.pair_capacity > cap) cap = s.pair_capacity;
+    if (cap > 0x7fffffffLL) cap = 0x7fffffffLL;
+    const size_t need = nr_workspace_bytes(&cfg, cap);
+    if (need > s.bytes) {
+        // growth: earlier calls on this stream may still use the old block
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return fail_cuda(e, "face_index_map_forward_safe");
-        if (!s.stats_host->overflow) return NR_OK;
-        if (s.stats_host->overflow == 2) {
-            s.general_faces = num_faces;
-            s.general_size = image_size;
-        }
-        cap = (long long)s.stats_host->total_pairs + 1024;
+        if (s.ptr) cudaFree(s.ptr);
+        s.ptr = nullptr;
+        s.bytes = 0;
+        s.pending = false;
+        e = cudaMalloc(&s.ptr, need + need / 4);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(scratch)");
+        s.bytes = need + need / 4;
     }
-    return fail(NR_ERR_WORKSPACE_TOO_SMALL, "pair list still overflowing after regrowth");
+    s.pair_capacity = cap;
+    if (s.general_faces == num_faces && s.general_size == image_size) cfg.flags |= NR_GENERAL_BINNING;
+    // the pinned statistics are owned by the call in flight until its event completes
+    const bool track = !s.pending;
+    int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, s.ptr, s.bytes, cap, track ? s.stats_host : nullptr,
+                                  track ? (void *)s.stats_event : nullptr, nullptr, nullptr, stream);
+    if (rc != NR_OK) return rc;
+    if (track) {
+        s.pending = true;
+        s.pend_faces = num_faces;
+        s.pend_size = image_size;
+    }
+    return NR_OK;
 }
 
 int nr_compute_weight_map(const float *faces, const int32_t *face_index_map, float *weight_map,

@@ -316,13 +316,18 @@ k_backward(const BackwardArgs a) {
                 const float *vtb = a.vt + (size_t)b * a.nvt * 2;
                 int tvid[3];
                 float u[3], v[3];
+                bool tex_ok = true;      // an out-of-range texture-vertex index contributes nothing (the forward drew black)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     tvid[k] = __ldg(fti + k);
+                    const bool ok = (unsigned)tvid[k] < (unsigned)a.nvt;
+                    tex_ok &= ok;
+                    if (!ok) tvid[k] = 0;
                     const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + tvid[k]);
                     u[k] = uv.x;
                     v[k] = uv.y;
                 }
+                if (tex_ok) {
                 float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f}, tw[4], g[3], rgb_tex[3];
                 float cw[3] = {1.f, 1.f, 1.f}, nrm[3] = {0.f, 0.f, 0.f};
                 const bool lit = LIT && a.lights.num > 0;
@@ -342,12 +347,13 @@ k_backward(const BackwardArgs a) {
                     const float gcw[3] = {g_lit[0] * rgb_tex[0], g_lit[1] * rgb_tex[1], g_lit[2] * rgb_tex[2]};
                     float cw2[3], gn[3];
                     light_weights(a.lights, b, a.B, nrm, cw2, gcw, gn);
-                    float *gvn = a.lights.grad_vnormals + (size_t)b * a.nv * 3;
+                    const size_t ovn = (size_t)b * a.nv * 3;
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
-                            if (gn[c] != 0.f) atomicAdd(gvn + 3 * (size_t)vid[k] + c, q[k] * gn[c]);
+                            if (gn[c] != 0.f)
+                                accumulate<DET>(a.lights.grad_vnormals, a.det_vn, ovn + 3 * (size_t)vid[k] + c, q[k] * gn[c], a.det_scale);
                 }
                 has_tex = true;
 #pragma unroll
@@ -362,6 +368,7 @@ k_backward(const BackwardArgs a) {
                         if (gv[k] != 0.f) accumulate<DET>(a.grad_vt, a.det_vt, o + 2 * (size_t)tvid[k] + 1, gv[k], a.det_scale);
                     }
                 }
+                }   // tex_ok
             }
             c0 = 3;
         }
@@ -486,6 +493,7 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     conv(a.det_verts, a.grad_verts, (size_t)a.B * a.nv * 3);
     conv(a.det_tex, a.grad_tex, (size_t)a.B * 3 * a.H * a.W);
     conv(a.det_vt, a.grad_vt, (size_t)a.B * a.nvt * 2);
+    conv(a.det_vn, a.lights.grad_vnormals, (size_t)a.B * a.nv * 3);
     return cudaGetLastError();
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ bool make_face_record(const float *__restrict__ vb, c
     r.q1 = r.q0;
     r.q2 = make_float4(0.f, __uint_as_float(DEAD_BBOX), 0.f, 0.f);
     if ((unsigned)i0 >= (unsigned)nv || (unsigned)i1 >= (unsigned)nv || (unsigned)i2 >= (unsigned)nv) {
-        hdr->bad_index = 1;
+        atomicOr(&hdr->bad_index, 1);
         return false;
     }
     const float x0 = vb[3 * i0], y0 = vb[3 * i0 + 1], z0 = vb[3 * i0 + 2];
@@ -717,8 +717,10 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
             k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_shift, a.tile_cursor, a.pairs,
                                                   a.pair_capacity, a.hdr);
         }
-        ProfScope p(PROF_SORT_LONG, stream);
-        k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
+        if (!a.unsorted) {
+            ProfScope p(PROF_SORT_LONG, stream);
+            k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
+        }
 
     }
     return cudaGetLastError();

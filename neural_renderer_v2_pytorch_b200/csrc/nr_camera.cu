@@ -13,14 +13,15 @@ namespace nr {
 
 constexpr int CAM_THREADS = 256;
 
+// shared != 0: `verts` is ONE mesh [1, nv, 3] seen by every camera (blockIdx.y still walks the views)
 __global__ void __launch_bounds__(CAM_THREADS)
 k_camera_forward(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
-                 float *__restrict__ out, int nv, int perspective, float width) {
+                 float *__restrict__ out, int nv, int perspective, float width, int shared) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nv) return;
     const float *R = rot + (size_t)b * 9, *E = eye + (size_t)b * 3;
-    const float *v = verts + ((size_t)b * nv + i) * 3;
+    const float *v = verts + ((size_t)(shared ? 0 : b) * nv + i) * 3;
     const float d0 = __fsub_rn(v[0], E[0]), d1 = __fsub_rn(v[1], E[1]), d2 = __fsub_rn(v[2], E[2]);
     float c[3];
 #pragma unroll
@@ -36,49 +37,35 @@ k_camera_forward(const float *__restrict__ verts, const float *__restrict__ rot,
     o[2] = c[2];
 }
 
-// grad_verts [B,nv,3] written; per-CTA partial sums of d loss / d R (9) and d loss / d eye (3) written
-// to partial [B, gridDim.x, 12] (summed by the caller in a fixed order: deterministic).
-__global__ void __launch_bounds__(CAM_THREADS)
-k_camera_backward(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
-                  const float *__restrict__ gout, float *__restrict__ gverts, float *__restrict__ partial, int nv,
-                  int perspective, float width) {
-    __shared__ float s_red[CAM_THREADS / 32][12];
-    const int b = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const float *R = rot + (size_t)b * 9, *E = eye + (size_t)b * 3;
-    float acc[12];
+// d loss / d (vertex, rotation, eye) of one (view, vertex): gd = gradient of the world-space vertex,
+// acc[0..8] += d rotation (row-major), acc[9..11] += d eye
+__device__ __forceinline__ void camera_backward_one(const float *R, const float *E, const float *v, const float *g,
+                                                    int perspective, float width, float gd[3], float acc[12]) {
+    const float d[3] = {v[0] - E[0], v[1] - E[1], v[2] - E[2]};
+    float gc[3] = {g[0], g[1], g[2]};
+    if (perspective) {
+        float c[3];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-    if (i < nv) {
-        const float *v = verts + ((size_t)b * nv + i) * 3;
-        const float *g = gout + ((size_t)b * nv + i) * 3;
-        const float d[3] = {v[0] - E[0], v[1] - E[1], v[2] - E[2]};
-        float gc[3] = {g[0], g[1], g[2]};
-        if (perspective) {
-            float c[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) c[r] = R[3 * r] * d[0] + R[3 * r + 1] * d[1] + R[3 * r + 2] * d[2];
-            const float iz = 1.f / c[2], izw = iz / width;
-            gc[2] = g[2] - (g[0] * c[0] + g[1] * c[1]) * iz * izw;
-            gc[0] = g[0] * izw;
-            gc[1] = g[1] * izw;
-        }
-        float gd[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) gd[j] = R[j] * gc[0] + R[3 + j] * gc[1] + R[6 + j] * gc[2];
-        float *gv = gverts + ((size_t)b * nv + i) * 3;
-        gv[0] = gd[0];
-        gv[1] = gd[1];
-        gv[2] = gd[2];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) acc[3 * r + j] = gc[r] * d[j];
-        acc[9] = -gd[0];
-        acc[10] = -gd[1];
-        acc[11] = -gd[2];
+        for (int r = 0; r < 3; ++r) c[r] = R[3 * r] * d[0] + R[3 * r + 1] * d[1] + R[3 * r + 2] * d[2];
+        const float iz = 1.f / c[2], izw = iz / width;
+        gc[2] = g[2] - (g[0] * c[0] + g[1] * c[1]) * iz * izw;
+        gc[0] = g[0] * izw;
+        gc[1] = g[1] * izw;
     }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gd[j] = R[j] * gc[0] + R[3 + j] * gc[1] + R[6 + j] * gc[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[3 * r + j] = gc[r] * d[j];
+    acc[9] = -gd[0];
+    acc[10] = -gd[1];
+    acc[11] = -gd[2];
+}
+
+// CTA sum of acc[12] -> partial[12] (fixed order)
+__device__ __forceinline__ void camera_block_sum(float acc[12], float (*s_red)[12], float *partial) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
         float x = acc[k];
@@ -89,7 +76,68 @@ k_camera_backward(const float *__restrict__ verts, const float *__restrict__ rot
     if (threadIdx.x < 12) {
         float x = 0.f;
         for (int w = 0; w < CAM_THREADS / 32; ++w) x += s_red[w][threadIdx.x];
-        partial[((size_t)b * gridDim.x + blockIdx.x) * 12 + threadIdx.x] = x;
+        partial[threadIdx.x] = x;
+    }
+    __syncthreads();
+}
+
+// grad_verts [B,nv,3] written; per-CTA partial sums of d loss / d R (9) and d loss / d eye (3) written
+// to partial [B, gridDim.x, 12] (summed by the caller in a fixed order: deterministic), unless it is null.
+__global__ void __launch_bounds__(CAM_THREADS)
+k_camera_backward(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
+                  const float *__restrict__ gout, float *__restrict__ gverts, float *__restrict__ partial, int nv,
+                  int perspective, float width) {
+    __shared__ float s_red[CAM_THREADS / 32][12];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+    if (i < nv) {
+        float gd[3];
+        camera_backward_one(rot + (size_t)b * 9, eye + (size_t)b * 3, verts + ((size_t)b * nv + i) * 3,
+                            gout + ((size_t)b * nv + i) * 3, perspective, width, gd, acc);
+        float *gv = gverts + ((size_t)b * nv + i) * 3;
+        gv[0] = gd[0];
+        gv[1] = gd[1];
+        gv[2] = gd[2];
+    }
+    if (partial) camera_block_sum(acc, s_red, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
+}
+
+// One mesh [1,nv,3] seen by B cameras: a thread owns a vertex and walks the views in order, so the gradient of
+// the shared mesh is summed in registers (fixed order, no [B,nv,3] intermediate, no atomics).
+__global__ void __launch_bounds__(CAM_THREADS)
+k_camera_backward_shared(const float *__restrict__ verts, const float *__restrict__ rot, const float *__restrict__ eye,
+                         const float *__restrict__ gout, float *__restrict__ gverts, float *__restrict__ partial, int B,
+                         int nv, int perspective, float width) {
+    __shared__ float s_red[CAM_THREADS / 32][12];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < nv;
+    float v[3] = {0.f, 0.f, 0.f}, sum[3] = {0.f, 0.f, 0.f};
+    if (in) {
+        v[0] = verts[3 * (size_t)i];
+        v[1] = verts[3 * (size_t)i + 1];
+        v[2] = verts[3 * (size_t)i + 2];
+    }
+    for (int b = 0; b < B; ++b) {
+        float acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+        if (in) {
+            float gd[3];
+            camera_backward_one(rot + (size_t)b * 9, eye + (size_t)b * 3, v, gout + ((size_t)b * nv + i) * 3, perspective,
+                                width, gd, acc);
+            sum[0] += gd[0];
+            sum[1] += gd[1];
+            sum[2] += gd[2];
+        }
+        if (partial) camera_block_sum(acc, s_red, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
+    }
+    if (in) {
+        gverts[3 * (size_t)i] = sum[0];
+        gverts[3 * (size_t)i + 1] = sum[1];
+        gverts[3 * (size_t)i + 2] = sum[2];
     }
 }
 
@@ -100,26 +148,32 @@ extern "C" {
 int nr_camera_partial_blocks(int32_t num_vertices) { return (num_vertices + nr::CAM_THREADS - 1) / nr::CAM_THREADS; }
 
 int nr_camera_forward(const float *vertices, const float *rotation, const float *eye, float *out, int32_t batch,
-                      int32_t num_vertices, int32_t perspective, float width, void *stream) {
+                      int32_t num_vertices, int32_t perspective, float width, int32_t shared_mesh, void *stream) {
     if (!vertices || !rotation || !eye || !out || batch < 0 || num_vertices < 0 || batch > 65535) return NR_ERR_INVALID_ARGUMENT;
     if (batch == 0 || num_vertices == 0) return NR_OK;
     dim3 grid(nr_camera_partial_blocks(num_vertices), batch);
+    nr::ProfScope p(nr::PROF_CAMERA_FORWARD, (cudaStream_t)stream);
     nr::k_camera_forward<<<grid, nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(vertices, rotation, eye, out, num_vertices,
-                                                                            perspective, width);
+                                                                            perspective, width, shared_mesh);
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }
 
 int nr_camera_backward(const float *vertices, const float *rotation, const float *eye, const float *grad_out,
                        float *grad_vertices, float *partial, int32_t batch, int32_t num_vertices,
-                       int32_t perspective, float width, void *stream) {
-    if (!vertices || !rotation || !eye || !grad_out || !grad_vertices || !partial || batch < 0 || num_vertices < 0 ||
-        batch > 65535)
+                       int32_t perspective, float width, int32_t shared_mesh, void *stream) {
+    if (!vertices || !rotation || !eye || !grad_out || !grad_vertices || batch < 0 || num_vertices < 0 || batch > 65535)
         return NR_ERR_INVALID_ARGUMENT;
     if (batch == 0 || num_vertices == 0) return NR_OK;
-    dim3 grid(nr_camera_partial_blocks(num_vertices), batch);
-    nr::k_camera_backward<<<grid, nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(vertices, rotation, eye, grad_out,
-                                                                             grad_vertices, partial, num_vertices,
-                                                                             perspective, width);
+    nr::ProfScope p(nr::PROF_CAMERA_BACKWARD, (cudaStream_t)stream);
+    if (shared_mesh) {
+        nr::k_camera_backward_shared<<<nr_camera_partial_blocks(num_vertices), nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(
+            vertices, rotation, eye, grad_out, grad_vertices, partial, batch, num_vertices, perspective, width);
+    } else {
+        dim3 grid(nr_camera_partial_blocks(num_vertices), batch);
+        nr::k_camera_backward<<<grid, nr::CAM_THREADS, 0, (cudaStream_t)stream>>>(vertices, rotation, eye, grad_out,
+                                                                                 grad_vertices, partial, num_vertices,
+                                                                                 perspective, width);
+    }
     return cudaGetLastError() == cudaSuccess ? NR_OK : NR_ERR_CUDA;
 }
 

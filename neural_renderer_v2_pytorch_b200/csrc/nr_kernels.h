@@ -10,7 +10,8 @@ constexpr int SMEM_SORT_CAP = 8192;
 
 // Brackets one launch with CUDA events while nr_profile_enable(1) is in force (nr_profile.cu).
 enum ProfSlot { PROF_MEMSET = 0, PROF_SETUP, PROF_SCAN, PROF_SCATTER, PROF_SORT_LONG, PROF_RASTER,
-                PROF_BACKWARD, PROF_DIFF_BACKWARD, PROF_WEIGHT_MAP };
+                PROF_BACKWARD, PROF_DIFF_BACKWARD, PROF_WEIGHT_MAP, PROF_RASTER_DENSE, PROF_CAMERA_FORWARD,
+                PROF_CAMERA_BACKWARD };
 class ProfScope {
 public:
     ProfScope(int slot, cudaStream_t stream);
@@ -34,6 +35,8 @@ struct BinningArgs {
     int sm_count;
     int one_cta_per_view;   // allow the single-kernel small-mesh path (k_bin_view)
     int tile_shift;         // log2 of the tile edge: 4 (16x16), or 3 (8x8, general path only); ntx counts these tiles
+    int unsorted;           // general path: leave the tile lists in scatter order (the dense raster kernel orders
+                            // the few candidates it needs itself)
 };
 bool binning_fits_one_cta_per_view(int nf, int R);
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
@@ -68,6 +71,7 @@ struct RasterArgs {
 };
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream);
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);
+cudaError_t launch_raster_dense(const RasterArgs &a, cudaStream_t stream);     // nr_raster_dense.cu
 
 struct BackwardArgs {
     const float *verts;     // [B, nv, 3]
@@ -83,7 +87,7 @@ struct BackwardArgs {
     float *grad_verts, *grad_tex, *grad_vt;
     // deterministic mode: 64-bit fixed-point accumulators (same shapes as the three gradients,
     // laid out back to back) and the power-of-two scale; null = float atomics
-    long long *det_verts, *det_tex, *det_vt;
+    long long *det_verts, *det_tex, *det_vt, *det_vn;   // det_vn: grad_vertex_normals (lights)
     float det_scale;
     LightArgs lights;
     int B, nv, nf, R, S, ntx, C, flags, nvt, H, W;

@@ -10,40 +10,9 @@
 //   rasterize_cuda_kernel.cu:246-308 weight map, rasterize.py:100-153 texture sampling,
 //   :240-242 silhouettes, :80-88 depth, :295-310 channel merge, :315-316 permute + flip,
 //   :321-328 2x2 anti-aliasing mean.
-#include "nr_kernels.h"
+#include "nr_shade.cuh"
 
 namespace nr {
-
-// Perspective-correct bilinear texture sample of one foreground pixel, rasterize.py:100-153.
-// q = weight map, z = face depths, uv = texel coordinates of the 3 face corners.
-__device__ __forceinline__ void sample_texture(const float *__restrict__ tex_b, int H, int W,
-                                               float eps, const float q[3], const float z[3],
-                                               const float u[3], const float v[3], float rgb[3]) {
-    const TexCoord tc = texel_coord(q, z, u, v, eps);
-    const float xf = tc.xf, yf = tc.yf;
-    const float xff = floorf(xf), yff = floorf(yf);
-    const float xcf = __fadd_rn(xff, 1.f), ycf = __fadd_rn(yff, 1.f);
-    const int xfi = (int)xff, yfi = (int)yff, xci = (int)xcf, yci = (int)ycf;
-    const float w1 = __fmul_rn(__fsub_rn(ycf, yf), __fsub_rn(xcf, xf));
-    const float w2 = __fmul_rn(__fsub_rn(ycf, yf), __fsub_rn(xf, xff));
-    const float w3 = __fmul_rn(__fsub_rn(yf, yff), __fsub_rn(xcf, xf));
-    const float w4 = __fmul_rn(__fsub_rn(yf, yff), __fsub_rn(xf, xff));
-    const int T = H * W;
-    const int i1 = yfi * W + xfi, i2 = yfi * W + xci, i3 = yci * W + xfi, i4 = yci * W + xci;
-    // to_map (utils.py:104-114) yields zero for a negative index; an index >= H*W is an
-    // IndexError in the reference and reads as zero here.
-    const bool ok1 = (unsigned)i1 < (unsigned)T, ok2 = (unsigned)i2 < (unsigned)T;
-    const bool ok3 = (unsigned)i3 < (unsigned)T, ok4 = (unsigned)i4 < (unsigned)T;
-    const float *p1 = tex_b + i1, *p2 = tex_b + i2, *p3 = tex_b + i3, *p4 = tex_b + i4;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int o = c * T;
-        const float t1 = ok1 ? __ldg(p1 + o) : 0.f, t2 = ok2 ? __ldg(p2 + o) : 0.f;
-        const float t3 = ok3 ? __ldg(p3 + o) : 0.f, t4 = ok4 ? __ldg(p4 + o) : 0.f;
-        rgb[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, t1), __fmul_rn(w2, t2)), __fmul_rn(w3, t3)),
-                           __fmul_rn(w4, t4));
-    }
-}
 
 // Conservative test "no pixel of the block [xa, xb] x [ya, yb] (pixel-centre coordinates) can pass
 // the reference's inside test for this face" (rasterize_cuda_kernel.cu:107-116).  The reference accepts
@@ -85,93 +54,6 @@ __device__ __forceinline__ bool block_outside_face(float x0, float y0, float x1,
 }
 
 
-// ---- output initialisation, done by the raster kernel itself --------------------------------------
-// The raster kernel is instruction-issue bound and leaves HBM idle, so everything that is a plain
-// fill rides along in it instead of running in front of it: the pixels of EMPTY tiles (face index -1,
-// image 0 or the background picture), and the caller's `zero` buffers (the gradient accumulators of the
-// coming backward).  Pixels of non-empty tiles are all written by the raster items, foreground or not.
-
-// value of rgb channel c behind a background pixel at OUTPUT position (u, v) of view b
-template <bool FULL>
-__device__ __forceinline__ float background_value(const RasterArgs &a, int b, int c, int u, int v) {
-    if (!FULL || !a.lights.backgrounds || c >= 3 || !(a.flags & FLAG_RGB)) return 0.f;
-    return __ldg(a.lights.backgrounds + (((size_t)b * 3 + c) * a.R + u) * a.R + v);
-}
-
-// `sparse`: write only what nr_rasterize_backward reads, i.e. not the face index of an empty tile, and
-// its internal-resolution image (anti-aliasing) only when a neighbouring tile is non-empty (the stencil
-// of a foreground pixel reaches one pixel into the next tile).
-template <bool AA, bool FULL, bool FINE>
-__device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int tx, int ty, int lane, bool sparse) {
-    const int R = a.R, S = a.S, C = a.C;
-    constexpr bool aa = AA;
-    constexpr int TSZ = FINE ? FINE_TILE : TILE;
-    bool need_fim = true, need_internal = true;
-    if (sparse) {
-        need_fim = false;
-        if (aa) {
-            const int *tc = a.tile_count + (size_t)b * a.ntx * a.ntx;
-            int any = 0;
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int x = tx + dx, y = ty + dy;
-                    if (x >= 0 && y >= 0 && x < a.ntx && y < a.ntx) any |= __ldg(tc + y * a.ntx + x);
-                }
-            need_internal = any != 0;
-        }
-    }
-    if (!FINE && (!FULL || ((R & 15) == 0 && !a.lights.backgrounds))) {
-        // vector path: a tile row is 64 aligned bytes in every plane; the flipped tile is again a tile
-        const int r = lane >> 2, q = (lane & 3) * 4;
-        const int4 m1 = make_int4(-1, -1, -1, -1);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (need_fim) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int y = ty * TILE + r + 8 * h;
-                __stcs(reinterpret_cast<int4 *>(a.fim + ((size_t)b * R + y) * R + tx * TILE + q), m1);
-            }
-        }
-        if (!a.images) return;
-        const int u0 = R - TILE - ty * TILE, v0 = R - TILE - tx * TILE;
-        float *full = aa ? a.internal : a.images;          // internal-resolution planes
-        if (!aa || need_internal) {
-            for (int c = 0; c < C; ++c) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    __stcs(reinterpret_cast<float4 *>(full + (((size_t)b * C + c) * R + u0 + r + 8 * h) * R + v0 + q), z);
-            }
-        }
-        if (aa) {
-            for (int i = lane; i < C * 16; i += 32) {
-                const int c = i >> 4, rr = (i >> 1) & 7, hh = (i & 1) * 4;
-                __stcs(reinterpret_cast<float4 *>(a.images + (((size_t)b * C + c) * S + (u0 >> 1) + rr) * S + (v0 >> 1) + hh), z);
-            }
-        }
-        return;
-    }
-    // (the launcher sends everything the vector path cannot do to the FULL variant)
-    if constexpr (FULL) {
-    for (int p = lane; p < TSZ * TSZ; p += 32) {
-        const int xi = tx * TSZ + (p & (TSZ - 1)), yi = ty * TSZ + p / TSZ;
-        if (xi >= R || yi >= R) continue;
-        if (need_fim) a.fim[((size_t)b * R + yi) * R + xi] = -1;
-        if (!a.images) continue;
-        const int u = R - 1 - yi, v = R - 1 - xi;
-        float *full = aa ? a.internal : a.images;
-        for (int c = 0; c < C; ++c) {
-            if (!aa || need_internal) full[(((size_t)b * C + c) * R + u) * R + v] = background_value<FULL>(a, b, c, u, v);
-            if (aa && !(u & 1) && !(v & 1)) {
-                // rasterize.py:323-328 on a pure-background quad
-                const float sum = __fadd_rn(__fadd_rn(__fadd_rn(background_value<FULL>(a, b, c, u, v), background_value<FULL>(a, b, c, u + 1, v)),
-                                                      background_value<FULL>(a, b, c, u, v + 1)), background_value<FULL>(a, b, c, u + 1, v + 1));
-                a.images[(((size_t)b * C + c) * S + (u >> 1)) * S + (v >> 1)] = __fmul_rn(sum, 0.25f);
-            }
-        }
-    }
-}
-}
-
 // Persistent kernel over the non-empty tiles.  The unit of work is one WARP = one 8x4 pixel block
 // of a tile, claimed with one atomicAdd (the next claim is in flight while the current block is
 // processed); the blocks of a tile are neighbours in the claim order, so its records are shared through
@@ -182,6 +64,20 @@ __device__ __forceinline__ void fill_empty_tile(const RasterArgs &a, int b, int 
 // Every pixel of the block is written (background included), see "output initialisation" above.
 constexpr int RASTER_WARPS = TILE_THREADS / 32;
 
+// NR_LAZY_Z: the z-test of a REGULAR candidate (face_z_regular, weights_one_sign: nothing cancels) is decided
+// with fast_zp() whenever the outcome is clear of its error bound, which it is for everything but near-ties:
+// the seven IEEE divisions of the reference's depth (~65 instructions) are then never executed.  The running
+// minimum may therefore be the cheap depth of the current winner (dexact == false); the first comparison that
+// is not clear recomputes it exactly from the winner's weights, so every DECISION equals the reference's.
+#ifndef NR_LAZY_Z
+#define NR_LAZY_Z 1
+#endif
+constexpr int REC_Q = NR_LAZY_Z ? 5 : 4;       // float4 per staged face
+
+__device__ __noinline__ float exact_zp_call(float w0, float w1, float w2, float z0, float z1, float z2) {
+    return exact_zp(w0, w1, w2, z0, z1, z2);
+}
+
 // Variants: RGB (texture sampling), AA (2x2 mean epilogue), FULL (everything optional: lights,
 // backgrounds, the weight / depth maps of rasterize_maps, resolutions that are no multiple of 16).
 // The plain variants leave that code out, which halves their size: at 75 KB the one-size kernel spent
@@ -191,7 +87,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_raster(const RasterArgs a) {
     // a tile is 16x16 pixels = 8 warp blocks (8x4 each), or in the FINE variants 8x8 = 2 blocks
     constexpr int TSZ = FINE ? FINE_TILE : TILE, BLK_SHIFT = FINE ? 1 : 3, BLKS = 1 << BLK_SHIFT;
-    __shared__ float4 s_rec[RASTER_WARPS][32][4];
+    __shared__ float4 s_rec[RASTER_WARPS][32][REC_Q];
     __shared__ uint32_t s_bb[RASTER_WARPS][32];
 
     // If the pair list did not fit the workspace, the lists are unusable: every block then scans ALL
@@ -207,56 +103,14 @@ k_raster(const RasterArgs a) {
     const bool pow2 = (R & (R - 1)) == 0;
     const float invR = 1.f / (float)R;          // exact for power-of-two R
     const unsigned lt_mask = (1u << lane) - 1u;
-    float4 (*my_rec)[4] = s_rec[wid];
+    float4 (*my_rec)[REC_Q] = s_rec[wid];
     uint32_t *my_bb = s_bb[wid];
 
-    // ---- fill items (stores only), interleaved with the raster items: claim i also performs fill item i,
-    // so the fills drain to HBM all along the kernel instead of in one burst that would stall every warp
-    // (a static share per warp was slower: the warps holding the heavy tiles kept their fills for the end).
-    // Fill item i < B * tiles: tile i if it is empty; then 4 KB chunks of the caller's zero buffers.
-    constexpr int ZCHUNK = 256;                 // int4 per chunk
-    const int nt = a.ntx * a.ntx, all_tiles = a.B * nt;
-    int zero_chunks[4] = {0, 0, 0, 0}, fill_items = all_tiles;
-    for (int k = 0; k < a.num_zero; ++k) {
-        zero_chunks[k] = (int)((a.zero_bytes[k] >> 4) / ZCHUNK) + 1;      // the last chunk also takes the tail words
-        fill_items += zero_chunks[k];
-    }
-    auto do_fill = [&](int i) {
-        if (i < all_tiles) {
-            if (__ldg(a.tile_count + i) != 0) return;
-            int b, tx, ty;
-            if ((a.ntx & (a.ntx - 1)) == 0) {       // power-of-two tile grid: shifts instead of divisions
-                const int sh = __ffs(a.ntx) - 1;
-                b = i >> (2 * sh);
-                ty = (i >> sh) & (a.ntx - 1);
-                tx = i & (a.ntx - 1);
-            } else {
-                b = i / nt;
-                const int tt = i - b * nt;
-                ty = tt / a.ntx;
-                tx = tt - ty * a.ntx;
-            }
-            fill_empty_tile<AA, FULL, FINE>(a, b, tx, ty, lane, a.sparse_maps != 0);
-            return;
-        }
-        int j = i - all_tiles;
-        for (int k = 0; k < a.num_zero; ++k) {
-            if (j >= zero_chunks[k]) {
-                j -= zero_chunks[k];
-                continue;
-            }
-            int4 *dst = reinterpret_cast<int4 *>(a.zero_ptr[k]);
-            const size_t n16 = a.zero_bytes[k] >> 4, base = (size_t)j * ZCHUNK;
-#pragma unroll
-            for (int s = 0; s < ZCHUNK / 32; ++s) {
-                const size_t idx = base + lane + 32 * s;
-                if (idx < n16) __stcs(dst + idx, make_int4(0, 0, 0, 0));
-            }
-            if (j == zero_chunks[k] - 1 && lane < (int)((a.zero_bytes[k] & 15) >> 2))
-                reinterpret_cast<int32_t *>(dst + n16)[lane] = 0;
-            return;
-        }
-    };
+    // ---- fill items (stores only, nr_shade.cuh), interleaved with the raster items: claim i also performs
+    // fill item i (a static share per warp was slower: the warps holding the heavy tiles kept their fills
+    // for the end)
+    const FillPlan plan = make_fill_plan(a);
+    const int fill_items = plan.fill_items;
 
     // Scheduling: the CTA claims EIGHT consecutive items (the blocks of one 16x16 tile) with one global
     // atomicAdd and its warps take them one by one from a shared cursor, so the blocks of a tile run on the
@@ -289,7 +143,7 @@ k_raster(const RasterArgs a) {
         }
         first = __shfl_sync(0xffffffffu, first, 0);
         if (first >= all_items) break;
-        if (first < fill_items) do_fill(first);
+        if (first < fill_items) do_fill_item<AA, FULL, FINE>(a, plan, first, lane);
     for (int item = first; item < min(first + GRAB, items); ++item) {
         const int4 e0 = tile_entry(tl, item >> BLK_SHIFT);
         const int sub = item & (BLKS - 1);
@@ -309,6 +163,7 @@ k_raster(const RasterArgs a) {
         const float yb = pow2 ? __fmul_rn((float)(2 * wy1 + 1 - R), invR) : pix_center(wy1, R);
 
         float depth_min = a.far_plane;
+        bool dexact = true;       // depth_min is the reference's value (not the cheap depth of the current winner)
         int best = -1;
         float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
 
@@ -349,6 +204,12 @@ k_raster(const RasterArgs a) {
                 my_rec[slot][1] = make_float4(x2, y2, __fsub_rn(x1, x0), __fsub_rn(y1, y0));
                 my_rec[slot][2] = make_float4(__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(x0, x2), __fsub_rn(y0, y2));
                 my_rec[slot][3] = make_float4(z0, z1, z2, __int_as_float(fid));
+#if NR_LAZY_Z
+                // reciprocal depths and the smallest corner depth of a regular face (NaN marks an irregular one)
+                const bool zreg = face_z_regular(z0, z1, z2);
+                my_rec[slot][4] = make_float4(fast_rcp(z0), fast_rcp(z1), fast_rcp(z2),
+                                              zreg ? fminf(z0, fminf(z1, z2)) : __int_as_float(0x7fc00000));
+#endif
                 // the face's pixel box (:94-97, exact by construction) as a bit mask over this block's 32
                 // pixels (bit = lane): the columns / rows it covers, relative to the block origin
                 const uint32_t bx = __float_as_uint(q2.y), by = __float_as_uint(q2.z);
@@ -381,17 +242,45 @@ k_raster(const RasterArgs a) {
                 const int j = __ffs(inside) - 1;
                 inside &= inside - 1;
                 const float4 D = my_rec[j][3];
+#if NR_LAZY_Z
+                const float4 E = my_rec[j][4];
+                // surely depth_min < every corner depth (:124-126 skips the face); false for an irregular face
+                if (depth_min * (1.f + FAST_Z_REL) < E.w) continue;
+                const float4 A = my_rec[j][0], Bq = my_rec[j][1];
+                float w0, w1, w2;
+                raw_weights(xp, yp, A.x, A.y, A.z, A.w, Bq.x, Bq.y, w0, w1, w2);
+                if (E.w == E.w && weights_one_sign(w0, w1, w2)) {
+                    const float zf = fast_zp(w0, w1, w2, E.x, E.y, E.z);
+                    const float m = 2.f * FAST_Z_REL * fmaxf(zf, depth_min);     // error of zf plus that of depth_min
+                    const float t = depth_min - a.delta;
+                    // (every comparison is false for a NaN: such a candidate takes the exact path)
+                    if (zf < a.near_plane - m || zf > a.far_plane + m || zf > t + m) continue;      // :140-148 reject it
+                    if (zf > a.near_plane + m && zf < a.far_plane - m && zf < t - m) {              // ... accept it
+                        depth_min = zf;
+                        dexact = false;
+                        best = __float_as_int(D.w);
+                        bw0 = w0; bw1 = w1; bw2 = w2;
+                        bz0 = D.x; bz1 = D.y; bz2 = D.z;
+                        continue;
+                    }
+                }
+                // not clear: the reference's own arithmetic, against the exact running minimum
+                if (!dexact) {
+                    depth_min = exact_zp_call(bw0, bw1, bw2, bz0, bz1, bz2);
+                    dexact = true;
+                }
+                if (depth_min < D.x && depth_min < D.y && depth_min < D.z) continue;      // :124-126
+                const float zp = exact_zp_call(w0, w1, w2, D.x, D.y, D.z);                 // :129-139
+#else
                 // :124-126
                 if (depth_min < D.x && depth_min < D.y && depth_min < D.z) continue;
                 const float4 A = my_rec[j][0], Bq = my_rec[j][1];
                 // :129-136
                 float w0, w1, w2;
                 raw_weights(xp, yp, A.x, A.y, A.z, A.w, Bq.x, Bq.y, w0, w1, w2);
-                const float ws = __fadd_rn(__fadd_rn(w0, w1), w2);
-                const float n0 = __fdiv_rn(w0, ws), n1 = __fdiv_rn(w1, ws), n2 = __fdiv_rn(w2, ws);
+                const float zp = exact_zp(w0, w1, w2, D.x, D.y, D.z);
+#endif
                 // :139-142
-                const float s = __fadd_rn(__fadd_rn(__fdiv_rn(n0, D.x), __fdiv_rn(n1, D.y)), __fdiv_rn(n2, D.z));
-                const float zp = __frcp_rn(s);
                 if (zp <= a.near_plane || a.far_plane <= zp) continue;
                 // :145-148
                 if (zp <= __fsub_rn(depth_min, a.delta)) {
@@ -404,104 +293,7 @@ k_raster(const RasterArgs a) {
             __syncwarp();
         }
         // ---------------------------------------------- epilogue: every pixel of the block is written
-        if (__ballot_sync(0xffffffffu, best >= 0) == 0u && !has_bg) {
-            // nothing but (black) background in this block
-            if (valid) {
-                a.fim[((size_t)b * R + yi) * R + xi] = -1;
-                if (!FULL || a.images) {
-                    const int u_ = R - 1 - yi, v_ = R - 1 - xi, C = a.C;
-                    float *full = (aa ? a.internal : a.images) + ((size_t)b * C * R + u_) * R + v_;
-                    const int plane = R * R;
-                    for (int c = 0; c < C; ++c) full[c * plane] = 0.f;
-                    if (aa && !(xi & 1) && !(yi & 1)) {
-                        float *half = a.images + ((size_t)b * C * a.S + (u_ >> 1)) * a.S + (v_ >> 1);
-                        const int plane_h = a.S * a.S;
-                        for (int c = 0; c < C; ++c) half[c * plane_h] = 0.f;
-                    }
-                }
-            }
-            continue;
-        }
-        const bool fg = valid && best >= 0;
-        float q[3] = {0.f, 0.f, 0.f};
-        if (fg) {
-            q[0] = bw0; q[1] = bw1; q[2] = bw2;
-            normalize_weights(q[0], q[1], q[2]);
-        }
-        const size_t pix = ((size_t)b * R + yi) * R + xi;
-        float dm = 0.f;
-        if (valid) a.fim[pix] = fg ? best : -1;
-        if (fg) {
-            if (FULL && a.wmap) {
-                float *w = a.wmap + pix * 3;
-                w[0] = q[0]; w[1] = q[1]; w[2] = q[2];
-            }
-            if ((a.flags & FLAG_DEPTH) || (FULL && a.dmap))
-                dm = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fdiv_rn(q[0], bz0), __fdiv_rn(q[1], bz1)), __fdiv_rn(q[2], bz2)));
-            if (FULL && a.dmap) a.dmap[pix] = dm;
-        }
-        if (!FULL || a.images) {
-            const int C = a.C, S = a.S;
-            const int u_ = R - 1 - yi, v_ = R - 1 - xi;   // flipped coordinates, rasterize.py:316
-            // one 64-bit pointer per output (this pixel, channel 0); channel c is a 32-bit plane offset away
-            float *p_full = (aa ? a.internal : a.images) + ((size_t)b * C * R + u_) * R + v_;
-            float *p_half = aa ? a.images + ((size_t)b * C * S + (u_ >> 1)) * S + (v_ >> 1) : nullptr;
-            const int plane_full = R * R, plane_half = S * S;
-            // one channel value of this pixel -> images (and the internal-resolution copy under AA)
-            auto put = [&](int c, float val) {
-                // background pixels show the background picture (black without one)
-                if (has_bg && !fg && valid) val = background_value<FULL>(a, b, c, u_, v_);
-                if (valid) p_full[c * plane_full] = val;
-                if (!aa) return;
-                // quad in flipped coordinates: F[2Y][2X] is (yi odd, xi odd); rasterize.py:323-328
-                const float px_ = __shfl_xor_sync(0xffffffffu, val, 1);   // same row, other column
-                const float py_ = __shfl_xor_sync(0xffffffffu, val, 8);   // other row, same column
-                const float pd_ = __shfl_xor_sync(0xffffffffu, val, 9);
-                if (valid && !(xi & 1) && !(yi & 1)) {
-                    // me = (even, even) -> F[2Y+1][2X+1]; py_ = (odd row, even col) -> F[2Y][2X+1]
-                    // px_ = (even row, odd col) -> F[2Y+1][2X]; pd_ = (odd, odd) -> F[2Y][2X]
-                    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(pd_, px_), py_), val);
-                    p_half[c * plane_half] = __fmul_rn(sum, 0.25f);
-                }
-            };
-            int c = 0;
-            if (RGB) {
-                float rgb[3] = {0.f, 0.f, 0.f};
-                if (fg) {
-                    const int32_t *fti = a.ft + 3 * (size_t)best;
-                    const float *vtb = a.vt + (size_t)b * a.nvt * 2;
-                    float u[3], v[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int t = __ldg(fti + k);
-                        const float2 uv = __ldg(reinterpret_cast<const float2 *>(vtb) + t);
-                        u[k] = uv.x;
-                        v[k] = uv.y;
-                    }
-                    const float z[3] = {bz0, bz1, bz2};
-                    sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
-                    if (FULL && a.lights.num > 0) {
-                        // smooth normal map (rasterize.py:186-187) and light accumulation (:252-283)
-                        float n[3] = {0.f, 0.f, 0.f}, cw[3];
-                        const float *vnb = a.lights.vnormals + (size_t)b * a.nv * 3;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const int vid = a.faces ? __ldg(a.faces + 3 * (size_t)best + k) : 3 * best + k;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) n[c] = __fadd_rn(n[c], __fmul_rn(q[k], __ldg(vnb + 3 * (size_t)vid + c)));
-                        }
-                        light_weights(a.lights, b, a.B, n, cw, nullptr, nullptr);
-                        rgb[0] = __fmul_rn(rgb[0], cw[0]); rgb[1] = __fmul_rn(rgb[1], cw[1]); rgb[2] = __fmul_rn(rgb[2], cw[2]);
-                    }
-                }
-                put(0, rgb[0]);
-                put(1, rgb[1]);
-                put(2, rgb[2]);
-                c = 3;
-            }
-            if (a.flags & FLAG_SIL) put(c++, fg ? 1.f : 0.f);
-            if (a.flags & FLAG_DEPTH) put(c++, dm);
-        }
+        shade_block<RGB, AA, FULL>(a, b, xi, yi, valid, best, bw0, bw1, bw2, bz0, bz1, bz2, has_bg);
     }   // items of this claim
     }   // claims
 }

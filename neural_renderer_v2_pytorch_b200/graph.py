@@ -48,12 +48,18 @@ def capture_step(step, params=(), warmup=3):
     mode = "global"
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         mode = "thread_local"
-    with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
-        out = step()
+    from . import rasterize as _rasterize
+    keep = _rasterize._capture_keepalive = []
+    try:
+        with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
+            out = step()
+    finally:
+        _rasterize._capture_keepalive = None
 
     def replay():
         graph.replay()
         return out
 
     replay.graph = graph
+    replay.workspaces = keep      # the rasterizer workspaces the graph replays on stay alive with it
     return replay

@@ -41,9 +41,23 @@ class SpecularLight(Light):
 
 
 def pack_lights(lights, batch, device):
-    """-> (types [L] int32, data [L,B,8] float32) on ``device`` (constants for autograd)."""
+    """-> (types [L] int32, data [L,B,8] float32) on ``device``.
+
+    The lights are CONSTANTS of the fused kernels: the backward returns gradients for the vertex normals (hence
+    the vertices) and the textures, not for ``color`` / ``direction`` / ``alpha`` (in the reference those flow
+    through torch ops, rasterize.py:256-283).  A light tensor that requires grad therefore raises instead of
+    silently receiving none."""
     types, rows = [], []
+    if len(lights) == 0:
+        # `lights=[]` is "lit by nothing": a black image in the reference (the accumulated colour weight stays 0)
+        lights = [AmbientLight(torch.zeros((batch, 3), dtype=torch.float32))]
     for light in lights:
+        for name in ("color", "direction", "alpha"):
+            t = getattr(light, name, None)
+            if torch.is_tensor(t) and t.requires_grad:
+                raise NotImplementedError(
+                    "gradients with respect to light.%s are not implemented by the fused kernels (lights are "
+                    "constants here); detach() it, or optimise it with the torch-op reference" % name)
         color = torch.as_tensor(light.color, dtype=torch.float32).to(device).detach()
         assert color.shape == (batch, 3), "light colour must be [batch, 3]"
         row = torch.zeros((batch, 8), dtype=torch.float32, device=device)

@@ -61,6 +61,31 @@ def share_across_views(param, local_views, group=None):
     return _ShareAcrossViews.apply(param, local_views, group)
 
 
+class _ShareAcrossRanks(torch.autograd.Function):
+    """Identity; the backward sums the gradient over the ranks (in place, on the stream of the backward, so a
+    captured step replays the collective too)."""
+
+    @staticmethod
+    def forward(ctx, param, group):
+        ctx.group = group
+        return param.view_as(param)
+
+    @staticmethod
+    def backward(ctx, grad):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            grad = grad.contiguous()
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=ctx.group)
+        return grad, None
+
+
+def share_across_ranks(param, group=None):
+    """Mark ``param`` (e.g. ONE mesh [1,nv,3] handed to ``Renderer.render*`` with per-view ``viewpoints`` [B,3]:
+    the fused camera transform projects it into the local views and sums its gradient over them) as shared by
+    every rank: after ``backward()`` ``param.grad`` is the sum over ALL views of the job, identical on every
+    rank.  The all-reduce moves 12*nv bytes (vertices) or 12*T (textures) per step."""
+    return _ShareAcrossRanks.apply(param, group)
+
+
 def allreduce_shared_grads(params, group=None):
     """Sum ``p.grad`` over ranks for parameters that every rank holds a replica of (when they were
     not routed through :func:`share_across_views`)."""

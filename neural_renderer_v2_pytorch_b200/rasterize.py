@@ -13,6 +13,7 @@ Differences from the reference that are deliberate (DESIGN.md "API notes"):
     (neural_renderer_chainer/rasterize.py:574-577) with a constant colour that is actually the colour.
 """
 import ctypes
+import os
 
 import torch
 
@@ -32,6 +33,14 @@ FORCE_FINE_TILES = False
 # Tile lists longer than this (nrBinStats.max_tile_faces of an earlier call) switch a shape that is binned
 # by the general path to 8x8 tiles.
 FINE_TILES_ABOVE = 192
+
+# test hook: True / False forces the face-parallel raster kernel for meshes of small triangles (nr_raster_dense.cu)
+# on / off whatever the statistics say; None = decide from the statistics of earlier calls
+FORCE_DENSE_RASTER = {"0": False, "1": True}.get(os.environ.get("NR_FORCE_DENSE_RASTER", ""))
+
+# A shape binned by the general path whose tile lists hold this many faces on average (nrBinStats.total_pairs over
+# the tiles of the batch, from an earlier call) is rasterized by the face-parallel kernel.
+DENSE_RASTER_ABOVE = 32
 
 # test hook: always bin with the general multi-kernel path (large meshes) instead of the one-kernel path
 FORCE_GENERAL_BINNING = False
@@ -78,6 +87,9 @@ class _Scratch:
         self.overflows = 0
         self.general_binning = set()        # (nf, R) whose views outgrew the one-kernel small-mesh binning
         self.fine_tiles = set()             # (nf, R) dense enough for 8x8 tiles (general path only)
+        self.dense = set()                  # (nf, R) of small triangles: face-parallel raster kernel
+        self.last_tiles = 1
+        self.bad_index = 0                  # nrBinStats.bad_index bits seen and not yet reported
         self.last_shape = None
         self.last_small = True
         ev = ctypes.c_void_p()
@@ -102,21 +114,43 @@ class _Scratch:
         elif L.nr_event_query(self.event) != 1:
             return
         self.pending = False
-        total, max_tile, overflow, _bad = self.stats.tolist()
-        if max_tile > FINE_TILES_ABOVE and self.last_shape is not None and not self.last_small:
-            self.fine_tiles.add(self.last_shape)
+        total, max_tile, overflow, bad = self.stats.tolist()
+        if self.last_shape is not None and not self.last_small:
+            if max_tile > FINE_TILES_ABOVE:
+                self.fine_tiles.add(self.last_shape)
+            if total >= DENSE_RASTER_ABOVE * self.last_tiles:
+                self.dense.add(self.last_shape)
+        self.bad_index |= bad
         if overflow:
             self.overflows += 1
             self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
             if overflow == 2:
                 self.general_binning.add(self.last_shape)
 
+    def report_bad_indices(self):
+        """An earlier call on this stream dropped faces (bit 0) or drew black pixels (bit 1) because of an index
+        outside its range: the reference raises IndexError for those (rasterize.py:232,246).  The synchronous
+        check (_validate_indices) catches them first on every eager call; this one covers calls replayed from a
+        CUDA graph, whose index tensors were edited after the capture."""
+        bad, self.bad_index = self.bad_index, 0
+        if bad:
+            what = " and ".join(n for bit, n in ((1, "faces (vertex index)"), (2, "faces_textures (texture-vertex index)")) if bad & bit)
+            raise IndexError("an earlier rasterize call on this stream had out-of-range indices in %s; "
+                             "those faces were dropped / drawn black" % what)
+
     def ensure(self, cfg, capacity):
         need = _lib.lib().nr_workspace_bytes(ctypes.byref(cfg), capacity)
         if self.workspace is None or self.workspace.numel() < need:
-            # torch's caching allocator hands out 512-byte aligned blocks
+            # torch's caching allocator hands out 512-byte aligned blocks.  (A workspace a captured CUDA graph
+            # replays on stays alive through the reference its replay object holds, see graph.capture_step.)
             self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
         self.pair_capacity = capacity
+
+
+# graph.capture_step sets this to a list while it captures: every workspace a captured forward bakes into the
+# graph is appended, and the replay object keeps the list, so a later, larger problem on the same stream cannot
+# free memory a graph still replays on
+_capture_keepalive = None
 
 
 def _make_config(B, nv, nf, S, flags, hp, nvt=0, H=0, W=0):
@@ -179,6 +213,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing:
             sc.poll()
+            sc.report_bad_indices()
         fim = torch.empty((B, R, R), dtype=torch.int32, device=dev)
         images = torch.empty((B, C, S, S), dtype=torch.float32, device=dev)
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
@@ -189,11 +224,14 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         shape = (cfg.num_faces, R)
         general = shape in sc.general_binning or FORCE_GENERAL_BINNING
         small = cfg.num_faces <= 8192 and ((R + 15) // 16) ** 2 <= 4096 and not general
-        fine = FORCE_FINE_TILES or (not small and shape in sc.fine_tiles)
+        dense = (not small and shape in sc.dense) if FORCE_DENSE_RASTER is None else bool(FORCE_DENSE_RASTER)
+        fine = not dense and (FORCE_FINE_TILES or (not small and shape in sc.fine_tiles))
         if general:
             cfg.flags |= _lib.NR_GENERAL_BINNING
         if fine:
             cfg.flags |= _lib.NR_FINE_TILES
+        if dense:
+            cfg.flags |= _lib.NR_DENSE_RASTER
         tile = 8 if fine else 16
         ntx = (R + tile - 1) // tile
         tile_list = torch.empty(8 + 16 * B * ntx * ntx, dtype=torch.int32, device=dev)
@@ -215,7 +253,9 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         if sparse and not want_maps and not fine:
             cfg.flags |= _lib.NR_SPARSE_MAPS     # fim / internal image are only handed to the backward
         if track:
-            sc.last_shape, sc.last_small = shape, small
+            sc.last_shape, sc.last_small, sc.last_tiles = shape, small, B * ((R + 15) // 16) ** 2
+        if capturing and _capture_keepalive is not None:
+            _capture_keepalive.append(ws)
         rc = L.nr_rasterize_forward(
             ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
             _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
@@ -229,14 +269,14 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         return images, internal, fim, wmap, dmap, (None if fine else tile_list)
 
 
-_validated_faces = {}
-
-
 def _validate_indices(idx, limit, what):
     """Index range check with the reference's error type (IndexError from tensor indexing,
-    rasterize.py:232,246).  Costs one device->host read per distinct index tensor, then cached."""
-    key = (idx.data_ptr(), idx._version, tuple(idx.shape), limit)
-    if _validated_faces.get(what) == key:
+    rasterize.py:232,246).  Costs one device->host read per index TENSOR and version of its contents: the
+    verdict is remembered on the tensor object itself (it dies with it, so a new tensor at a recycled address
+    is checked again).  Safety does not rest on this check: the kernels test every index themselves
+    (nrBinStats.bad_index, reported by the next call on the stream)."""
+    key = (idx._version, limit)
+    if getattr(idx, "_nr_validated", None) == key:
         return
     if idx.is_cuda and torch.cuda.is_current_stream_capturing():
         return      # cannot read back during capture; the kernels drop out-of-range faces anyway
@@ -244,7 +284,11 @@ def _validate_indices(idx, limit, what):
         lo, hi = int(idx.min()), int(idx.max())
         if lo < 0 or hi >= limit:
             raise IndexError("%s reference index %d outside [0, %d)" % (what, hi if hi >= limit else lo, limit))
-    _validated_faces[what] = key
+    if idx.is_cuda:         # a CPU tensor may share memory with a numpy array edited behind torch's back
+        try:
+            idx._nr_validated = key
+        except (AttributeError, RuntimeError):
+            pass
 
 
 class _Rasterize(torch.autograd.Function):
@@ -383,7 +427,7 @@ def _prepare(vertices, faces, params, hyperparams):
     cfg = _make_config(B, nv, nf, int(hyperparams.image_size), _flags_of(hyperparams), hyperparams,
                        nvt, H, W)
     light_pack = vn = None
-    if hyperparams.draw_rgb and params.lights:
+    if hyperparams.draw_rgb and params.lights is not None:      # an empty list renders black, rasterize.py:252-283
         # shading: per-vertex normals by differentiable torch ops (O(nv + nf)), the per-pixel part in the kernels
         light_pack = light_lib.pack_lights(params.lights, B, dev)
         vn = light_lib.vertex_normals(vertices, faces_d)

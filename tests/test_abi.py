@@ -40,7 +40,7 @@ def test_python_binding_lists_every_symbol(lib_path):
     L = _lib.lib()
     for s in _lib.SYMBOLS:
         assert hasattr(L, s)
-    assert L.nr_abi_version() == _lib.ABI_VERSION == 2
+    assert L.nr_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_torch_in_the_abi(lib_path):

@@ -99,6 +99,14 @@ def test_config4_window_against_the_oracle(nr):
     finally:
         rz.FORCE_FINE_TILES = False
     assert torch.equal(fim, fine)
+    # the face-parallel raster kernel (unsorted lists, shared-memory z-buffer, exact replay of contested pixels)
+    for force in (True, False):
+        rz.FORCE_DENSE_RASTER = force
+        try:
+            other = nr.rasterize_maps(v, faces, nr.RasterizeParam(), hp)["face_index_map"]
+        finally:
+            rz.FORCE_DENSE_RASTER = None
+        assert torch.equal(fim, other), "dense=%s: %d px differ" % (force, int((fim != other).sum()))
     one = nr.rasterize_maps(v[1:2], faces, nr.RasterizeParam(), hp)["face_index_map"]
     assert torch.equal(fim[1:2], one)
     fv = v[:, faces.long()]                                           # [2, nf, 3, 3]

@@ -101,6 +101,26 @@ def test_golden_case_with_fine_tiles(nr, name):
         grad_close(vt.grad.cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_golden_case_with_dense_raster(nr, name):
+    """The face-parallel raster kernel for meshes of small triangles (nr_raster_dense.cu: unsorted tile lists,
+    shared-memory z-buffer, exact replay of contested pixels) against the same reference fixtures: face_index_map
+    bit for bit, images and every gradient."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    rz.FORCE_DENSE_RASTER = True
+    try:
+        images, v, tex, vt, maps = run_cuda(nr, d)
+    finally:
+        rz.FORCE_DENSE_RASTER = None
+    assert np.array_equal(maps["face_index_map"].cpu().numpy(), d["face_index_map"])
+    np.testing.assert_allclose(images.detach().cpu().numpy(), d["images"], rtol=1e-5, atol=1e-6)
+    grad_close(v.grad.cpu().numpy(), d["grad_vertices"], "grad_vertices")
+    if tex is not None:
+        grad_close(tex.grad.cpu().numpy(), d["grad_textures"], "grad_textures")
+        grad_close(vt.grad.cpu().numpy(), d["grad_vertices_textures"], "grad_vertices_textures")
+
+
 @pytest.mark.parametrize("name", ["lit_rgb_48", "lit_rgb_aa_24"])
 def test_lights_golden(nr, name):
     """Directional + Ambient + Specular lights (rasterize.py:252-283) fused into the kernels vs the
@@ -234,16 +254,19 @@ def _check_vs_oracle(nr, faces_np, R, **kw):
     B, nf = faces_np.shape[:2]
     v = torch.from_numpy(np.ascontiguousarray(faces_np, dtype=np.float32)).reshape(B, nf * 3, 3).cuda()
     idx = torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3).cuda()
-    for general, fine in ((False, False), (True, False), (True, True)):
-        rz.FORCE_GENERAL_BINNING, rz.FORCE_FINE_TILES = general, fine
+    for general, fine, dense in ((False, False, False), (True, False, False), (True, True, False), (True, False, True)):
+        rz.FORCE_GENERAL_BINNING, rz.FORCE_FINE_TILES, rz.FORCE_DENSE_RASTER = general, fine, dense
         try:
             hp = nr.RasterizeHyperparam(image_size=R, near=kw.get("near", 0.1), far=kw.get("far", 100.0), anti_aliasing=False,
                                         draw_backside=kw.get("backside", True), draw_rgb=False, draw_depth=False)
             maps = nr.rasterize_maps(v, idx, nr.RasterizeParam(), hp)
         finally:
             rz.FORCE_GENERAL_BINNING = rz.FORCE_FINE_TILES = False
-        assert np.array_equal(maps["face_index_map"].cpu().numpy(), want), "fused forward (general=%s, fine=%s): face_index_map" % (general, fine)
-        assert np.array_equal(maps["weight_map"].cpu().numpy(), want_wm), "fused forward (general=%s, fine=%s): weight_map" % (general, fine)
+            rz.FORCE_DENSE_RASTER = None
+        got = maps["face_index_map"].cpu().numpy()
+        assert np.array_equal(got, want), "fused forward (general=%s, fine=%s, dense=%s): face_index_map differs in %d px" % (
+            general, fine, dense, (got != want).sum())
+        assert np.array_equal(maps["weight_map"].cpu().numpy(), want_wm), "fused forward (general=%s, fine=%s, dense=%s): weight_map" % (general, fine, dense)
         assert np.array_equal(maps["images"][:, 0].flip(1, 2).cpu().numpy(), (want >= 0).astype(np.float32))
     return fim
 
@@ -745,7 +768,8 @@ def test_reference_backward_case1_with_its_own_target(nr):
 
 
 @pytest.mark.parametrize("S,aa,fine,general", [(64, False, False, False), (36, True, False, False), (40, True, True, True),
-                                                (50, False, True, True), (64, True, False, True)])
+                                                (50, False, True, True), (64, True, False, True), (50, False, "dense", True),
+                                                (36, True, "dense", True)])
 def test_kernels_stay_inside_their_buffers(nr, S, aa, fine, general):
     """No sanitizer on this pool: every output of the forward / backward is carved out of a larger
     poisoned allocation and the guard words on both sides must survive (vector and scalar fill paths,
@@ -765,8 +789,10 @@ def test_kernels_stay_inside_their_buffers(nr, S, aa, fine, general):
     vt = torch.from_numpy(vt_np)[None].repeat(B, 1, 1).cuda()
     ft = torch.from_numpy(ft_np).cuda()
     R = 2 * S if aa else S
+    dense, fine = fine == "dense", fine is True
     flags = (_lib.NR_DRAW_RGB | _lib.NR_DRAW_SILHOUETTES | _lib.NR_DRAW_BACKSIDE | (_lib.NR_ANTI_ALIASING if aa else 0) |
-             (_lib.NR_FINE_TILES if fine else 0) | (_lib.NR_GENERAL_BINNING if general else 0))
+             (_lib.NR_FINE_TILES if fine else 0) | (_lib.NR_GENERAL_BINNING if general else 0) |
+             (_lib.NR_DENSE_RASTER if dense else 0))
     cfg = _lib.RasterConfig(batch=B, num_vertices=v.shape[1], num_faces=faces.shape[0], image_size=S, flags=flags,
                             near_plane=0.1, far_plane=100., eps=1e-5, depth_min_delta=1e-4, num_tex_vertices=vt.shape[1],
                             tex_height=tex.shape[2], tex_width=tex.shape[3])

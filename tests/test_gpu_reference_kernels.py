@@ -42,6 +42,22 @@ def ours(nr, faces, S, near, far, bs):
     return fim.reshape(B, S, S).cpu().numpy(), wm.reshape(B, S, S, 3).cpu().numpy()
 
 
+def ours_dense(nr, faces, S, near, far, bs):
+    """The same maps from the fused forward with the face-parallel raster kernel (nr_raster_dense.cu)."""
+    from neural_renderer_v2_pytorch_b200 import rasterize as rz
+    B, nf = faces.shape[:2]
+    v = torch.from_numpy(np.ascontiguousarray(faces, dtype=np.float32)).reshape(B, nf * 3, 3).cuda()
+    idx = torch.arange(nf * 3, dtype=torch.int32).reshape(nf, 3).cuda()
+    rz.FORCE_DENSE_RASTER = True
+    try:
+        hp = nr.RasterizeHyperparam(image_size=S, near=near, far=far, anti_aliasing=False, draw_backside=bool(bs),
+                                    draw_rgb=False, draw_depth=False)
+        maps = nr.rasterize_maps(v, idx, nr.RasterizeParam(), hp)
+    finally:
+        rz.FORCE_DENSE_RASTER = None
+    return maps["face_index_map"].cpu().numpy(), maps["weight_map"].cpu().numpy()
+
+
 @pytest.mark.parametrize("name", sorted(mk.ref_kernel_inputs().keys()))
 def test_three_way(refmod, nr, name):
     faces, S, near, far, bs = mk.ref_kernel_inputs()[name]
@@ -53,6 +69,9 @@ def test_three_way(refmod, nr, name):
     assert np.array_equal(wm_c, wm_ref), "C oracle weight map != reference kernel"
     assert np.array_equal(fim_o, fim_ref), "CUDA path != reference kernel: %d px" % (fim_o != fim_ref).sum()
     assert np.array_equal(wm_o, wm_ref), "CUDA path weight map != reference kernel"
+    fim_d, wm_d = ours_dense(nr, faces, S, near, far, bs)
+    assert np.array_equal(fim_d, fim_ref), "dense raster kernel != reference kernel: %d px" % (fim_d != fim_ref).sum()
+    assert np.array_equal(wm_d, wm_ref), "dense raster kernel weight map != reference kernel"
 
 
 def test_full_size_teapot_512(refmod, nr):
@@ -63,6 +82,9 @@ def test_full_size_teapot_512(refmod, nr):
     assert (fim_ref >= 0).mean() > 0.05
     assert np.array_equal(fim_o, fim_ref), "%d px differ" % (fim_o != fim_ref).sum()
     assert np.array_equal(wm_o, wm_ref)
+    fim_d, wm_d = ours_dense(nr, faces, 512, 0.1, 100.0, 1)
+    assert np.array_equal(fim_d, fim_ref), "dense raster kernel: %d px differ" % (fim_d != fim_ref).sum()
+    assert np.array_equal(wm_d, wm_ref)
 
 
 def test_dense_random_1024(refmod, nr):
@@ -72,3 +94,6 @@ def test_dense_random_1024(refmod, nr):
     fim_o, wm_o = ours(nr, faces, 1024, 0.1, 100.0, 1)
     assert np.array_equal(fim_o, fim_ref), "%d px differ" % (fim_o != fim_ref).sum()
     assert np.array_equal(wm_o, wm_ref)
+    fim_d, wm_d = ours_dense(nr, faces, 1024, 0.1, 100.0, 1)
+    assert np.array_equal(fim_d, fim_ref), "dense raster kernel: %d px differ" % (fim_d != fim_ref).sum()
+    assert np.array_equal(wm_d, wm_ref)
