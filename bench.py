@@ -417,7 +417,7 @@ def run_ours(args):
     cnt = (ctypes.c_int32 * _lib.NR_PROF_SLOTS)()
     L.nr_profile_collect(ms, cnt)
     kern = {n: (ms[i] / cnt[i]) for i, n in enumerate(_lib.PROF_SLOT_NAMES) if cnt[i]}
-    if "setup_count" in kern and "scan_tiles" not in kern and "raster_dense" not in kern:
+    if "setup_count" in kern and "scan_tiles" not in kern:
         kern["bin_view"] = kern.pop("setup_count")      # small meshes: the one-kernel cluster binning uses this slot
     # kernels of this library per step (memset nodes not counted)
     launches_per_step = sum(cnt[i] for i, n in enumerate(_lib.PROF_SLOT_NAMES) if n != "memset") / args.steps
@@ -511,10 +511,23 @@ def run_ours(args):
         finish()
         return
 
+    # statistics of the last forward (nrBinStats; their meaning depends on the path, see include/nr_b200.h)
+    bin_stats = None
+    try:
+        from neural_renderer_v2_pytorch_b200 import rasterize as _rz
+        for (di, _), sc in _rz._Scratch._cache.items():
+            if di == dev.index and sc.last_shape is not None:
+                sc.poll(block=True)
+                t_, m_, o_, b_ = sc.stats.tolist()
+                bin_stats = {"total_pairs": t_, "max_tile_faces": m_, "overflow": o_, "bad_index": b_,
+                             "path": "zbuf" if sc.last_dense else ("one-kernel binning" if sc.last_small else "general binning")}
+    except Exception:
+        pass
+
     # ---- roofline of the dominant kernel
     peak, peak_src = peaks()
     fwd_b, bwd_b = algorithmic_bytes(inp["nv"], inp["nf"], inp["T"], R * R, C, S)
-    shares = {"raster": fwd_b * B, "raster_dense": fwd_b * B, "backward": bwd_b * B}
+    shares = {"raster": fwd_b * B, "zbuf_faces": fwd_b * B, "backward": bwd_b * B}
     dom = max((k for k in kern if k in shares), key=lambda k: kern[k])
     achieved = shares[dom] / (kern[dom] / 1e3) / 1e9
     traffic, traffic_src = None, None
@@ -557,6 +570,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "kernels_ms": {k: round(v, 4) for k, v in kern.items()},
+        "bin_stats": bin_stats,
     }
     if cpu:
         line["cpu_baseline"] = cpu

@@ -66,10 +66,14 @@ enum {
                                  be passed to nr_rasterize_backward (pass NULL); NR_SPARSE_MAPS is ignored. */
 #define NR_GENERAL_BINNING 64 /* forward: never take the one-kernel small-mesh binning path (see nrBinStats) */
 #define NR_DENSE_RASTER 512   /* forward: meshes of SMALL triangles (nrBinStats.total_pairs of an earlier call >= ~32 per
-                                 tile on average, a few tiles per face): general binning WITHOUT the per-tile sort, and
-                                 the face-parallel raster kernel (one CTA per 16x16 tile, one thread per face, z-buffer
-                                 in shared memory, exact resolution of contested pixels: nr_raster_dense.cu).  Same
-                                 results bit for bit; implies NR_GENERAL_BINNING, excludes NR_FINE_TILES. */
+                                 tile on average, a few tiles per face): no tile lists at all, one thread per face
+                                 merging (depth, face) into a 64-bit global z-buffer with atomicMin, exact replay of
+                                 the reference's sequential scan for contested pixels (nr_raster_zbuf.cu).  Same
+                                 results bit for bit.  nr_workspace_bytes depends on this flag; nrBinStats then
+                                 reports total_pairs = contested pixels, max_tile_faces = faces whose pixel box is
+                                 above 4096 pixels (more than a few per cent of the faces: drop the flag),
+                                 overflow = 1 when the candidate pool (pair_capacity / 4 entries) was too small
+                                 (still exact, slower). */
 
 /* Mirrors RasterizeHyperparam (rasterize_param.py:13-33) plus the tensor extents. */
 typedef struct nrRasterConfig {
@@ -158,10 +162,10 @@ NR_API int nr_event_query(void *event); /* 1 complete, 0 not yet, -1 error */
  * bracketed by CUDA events on its launch stream.  nr_profile_collect synchronises those events and
  * ADDS the elapsed milliseconds / launch counts per slot into ms[NR_PROF_SLOTS] / launches[...]
  * (slots: 0 memset, 1 setup_count, 2 scan_tiles, 3 scatter, 4 sort_long, 5 raster, 6 backward,
- * 7 differentiation_backward, 8 weight_map_compat, 9 raster_dense, 10 camera_forward, 11 camera_backward),
- * then forgets them.
+ * 7 differentiation_backward, 8 weight_map_compat, 9 zbuf_faces, 10 camera_forward, 11 camera_backward,
+ * 12 zbuf_resolve, 13 zbuf_shade), then forgets them.
  */
-#define NR_PROF_SLOTS 12
+#define NR_PROF_SLOTS 14
 NR_API int nr_profile_enable(int on);
 NR_API int nr_profile_collect(float *ms, int32_t *launches);
 

@@ -36,10 +36,10 @@ SYMBOLS = (
     "nr_profile_enable", "nr_profile_collect", "nr_camera_partial_blocks", "nr_camera_forward",
     "nr_camera_backward",
 )
-NR_PROF_SLOTS = 12
+NR_PROF_SLOTS = 14
 PROF_SLOT_NAMES = ("memset", "setup_count", "scan_tiles", "scatter", "sort_long", "raster", "backward",
-                   "differentiation_backward", "weight_map_compat", "raster_dense", "camera_forward",
-                   "camera_backward")
+                   "differentiation_backward", "weight_map_compat", "zbuf_faces", "camera_forward",
+                   "camera_backward", "zbuf_resolve", "zbuf_shade")
 
 
 class RasterConfig(ctypes.Structure):

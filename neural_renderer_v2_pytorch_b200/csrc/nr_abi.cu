@@ -29,8 +29,53 @@ struct Carve {
     nr::FaceRec *rec;
     int32_t *pairs;
     int32_t *tile_list;
+    // z-buffer path (NR_DENSE_RASTER)
+    unsigned *zb_bitmap, *zb_coarse;
+    uint2 *zb_box;
+    unsigned long long *zbuf;
+    int *zb_head, *zb_pix_of;
+    int4 *zb_nodes;
+    int zb_wpr, zb_crows, zb_slot_cap, zb_node_cap;
     size_t bytes;
 };
+
+// NR_DENSE_RASTER: header | contested-pixel bitmap (adjacent: one memset clears both) | z-buffer | list heads |
+// pixel of every slot | candidate nodes | tile list.  pair_capacity counts 4-byte units as in the tile pipeline:
+// a quarter of it is the number of 16-byte candidate nodes (and of contested pixels) the call can hold.
+Carve carve_dense(void *base, int B, int nf, int R, long long pair_capacity) {
+    const int ntx = (R + nr::TILE - 1) / nr::TILE;
+    const size_t nt = (size_t)B * ntx * ntx;
+    char *p = (char *)base;
+    size_t off = 0;
+    Carve c;
+    memset(&c, 0, sizeof(c));
+    c.hdr = (nr::BinHeader *)(p + off);
+    off += sizeof(nr::BinHeader);
+    c.zb_wpr = (R + 31) / 32;
+    c.zb_crows = (R + 7) / 8;
+    c.zb_bitmap = (unsigned *)(p + off);
+    off += (size_t)B * R * c.zb_wpr * sizeof(unsigned);
+    c.zb_coarse = (unsigned *)(p + off);
+    off = align256(off + (size_t)B * c.zb_crows * c.zb_wpr * sizeof(unsigned));
+    c.zb_box = (uint2 *)(p + off);
+    off = align256(off + (size_t)B * nf * sizeof(uint2));
+    c.zbuf = (unsigned long long *)(p + off);
+    off = align256(off + (size_t)B * R * R * sizeof(unsigned long long));
+    long long cap = pair_capacity / 4;
+    if (cap < 1024) cap = 1024;
+    if (cap > 0x3fffffffLL) cap = 0x3fffffffLL;
+    c.zb_slot_cap = c.zb_node_cap = (int)cap;
+    c.zb_head = (int *)(p + off);
+    off = align256(off + (size_t)cap * sizeof(int));
+    c.zb_pix_of = (int *)(p + off);
+    off = align256(off + (size_t)cap * sizeof(int));
+    c.zb_nodes = (int4 *)(p + off);
+    off = align256(off + (size_t)cap * sizeof(int4));
+    c.tile_list = (int32_t *)(p + off);
+    off = align256(off + (nr::TILE_LIST_HDR + nr::TILE_ENTRY_INTS * nr::TILE_CLASSES * nt) * sizeof(int32_t));
+    c.bytes = off;
+    return c;
+}
 
 // header and tile_count must be adjacent (one memset clears both)
 Carve carve(void *base, int B, int nf, int R, long long pair_capacity, int tile) {
@@ -39,6 +84,7 @@ Carve carve(void *base, int B, int nf, int R, long long pair_capacity, int tile)
     char *p = (char *)base;
     size_t off = 0;
     Carve c;
+    memset(&c, 0, sizeof(c));
     c.hdr = (nr::BinHeader *)(p + off);
     off += sizeof(nr::BinHeader);
     c.tile_count = (int *)(p + off);
@@ -159,6 +205,7 @@ size_t nr_deterministic_scratch_bytes(const nrRasterConfig *cfg) {
 size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
     if (!cfg) return 0;
     const int R = cfg->image_size * ((cfg->flags & NR_ANTI_ALIASING) ? 2 : 1);
+    if (cfg->flags & NR_DENSE_RASTER) return carve_dense(nullptr, cfg->batch, cfg->num_faces, R, pair_capacity).bytes;
     return carve(nullptr, cfg->batch, cfg->num_faces, R, pair_capacity, tile_edge(cfg)).bytes;
 }
 
@@ -190,7 +237,11 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
         if ((long long)cfg->batch * ntx_ * ntx_ * 8 > 0x3fffffffLL || (long long)cfg->batch * cfg->num_faces > 0x7fffffffLL)
             return fail(NR_ERR_INVALID_ARGUMENT, "batch x tiles (or batch x faces) too large for one call: split the batch");
     }
-    const Carve c = carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity, tile);
+    const bool dense = (cfg->flags & NR_DENSE_RASTER) != 0;
+    if (dense && (long long)cfg->batch * R * R > 0x7fffffffLL)
+        return fail(NR_ERR_INVALID_ARGUMENT, "NR_DENSE_RASTER: batch x pixels too large for one call: split the batch");
+    const Carve c = dense ? carve_dense(workspace, cfg->batch, cfg->num_faces, R, pair_capacity)
+                          : carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity, tile);
     if (c.bytes > workspace_bytes) return fail(NR_ERR_WORKSPACE_TOO_SMALL, "workspace smaller than nr_workspace_bytes()");
     if (cfg->batch == 0) return NR_OK;
 
@@ -213,9 +264,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ba.hdr = c.hdr;
     ba.tile_list = tile_list ? tile_list : c.tile_list;
     ba.sm_count = sm_count_cached();
-    const bool dense = (cfg->flags & NR_DENSE_RASTER) != 0;
     ba.one_cta_per_view = (cfg->flags & (NR_GENERAL_BINNING | NR_FINE_TILES | NR_DENSE_RASTER)) ? 0 : 1;
-    ba.unsorted = dense ? 1 : 0;
 
     nr::RasterArgs ra;
     ra.rec = c.rec;
@@ -249,6 +298,18 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.internal = images_internal;
     ra.faces = faces;
     ra.nv = cfg->num_vertices;
+    ra.verts = vertices;
+    ra.zbuf = c.zbuf;
+    ra.zb_bitmap = c.zb_bitmap;
+    ra.zb_coarse = c.zb_coarse;
+    ra.zb_box = c.zb_box;
+    ra.zb_wpr = c.zb_wpr;
+    ra.zb_crows = c.zb_crows;
+    ra.zb_head = c.zb_head;
+    ra.zb_pix_of = c.zb_pix_of;
+    ra.zb_nodes = c.zb_nodes;
+    ra.zb_slot_cap = c.zb_slot_cap;
+    ra.zb_node_cap = c.zb_node_cap;
     ra.lights = nr::LightArgs{0, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (lights && lights->num_lights > 0 && rgb) {
         if (!lights->types || !lights->data || !lights->vertex_normals)
@@ -274,9 +335,13 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
 
     cudaError_t e;
     if ((e = nr::launch_background_fill(ra, stream)) != cudaSuccess) return fail_cuda(e, "map fill");
-    e = nr::launch_binning(ba, stream);
-    if (e != cudaSuccess) return fail_cuda(e, "binning");
-    e = dense ? nr::launch_raster_dense(ra, stream) : nr::launch_raster(ra, stream);
+    if (dense) {
+        e = nr::launch_raster_zbuf(ra, stream);
+    } else {
+        e = nr::launch_binning(ba, stream);
+        if (e != cudaSuccess) return fail_cuda(e, "binning");
+        e = nr::launch_raster(ra, stream);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "raster");
     if (stats_host) {
         e = cudaMemcpyAsync(stats_host, c.hdr, sizeof(nrBinStats), cudaMemcpyDeviceToHost, stream);

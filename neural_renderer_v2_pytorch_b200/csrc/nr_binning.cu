@@ -20,68 +20,6 @@
 
 namespace nr {
 
-// Record of face f of one view (vb = that view's vertices) and its exact pixel box; returns false for
-// a face no pixel can accept (its record then carries the dead box).
-__device__ __forceinline__ bool make_face_record(const float *__restrict__ vb, const int32_t *__restrict__ faces,
-                                                 int f, int nv, int R, int draw_backside, FaceRec &r, int &xlo,
-                                                 int &xhi, int &ylo, int &yhi, BinHeader *__restrict__ hdr) {
-    int i0, i1, i2;
-    if (faces) {
-        i0 = __ldg(faces + 3 * f + 0);
-        i1 = __ldg(faces + 3 * f + 1);
-        i2 = __ldg(faces + 3 * f + 2);
-    } else {
-        i0 = 3 * f;
-        i1 = i0 + 1;
-        i2 = i0 + 2;
-    }
-    r.q0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    r.q1 = r.q0;
-    r.q2 = make_float4(0.f, __uint_as_float(DEAD_BBOX), 0.f, 0.f);
-    if ((unsigned)i0 >= (unsigned)nv || (unsigned)i1 >= (unsigned)nv || (unsigned)i2 >= (unsigned)nv) {
-        atomicOr(&hdr->bad_index, 1);
-        return false;
-    }
-    const float x0 = vb[3 * i0], y0 = vb[3 * i0 + 1], z0 = vb[3 * i0 + 2];
-    const float x1 = vb[3 * i1], y1 = vb[3 * i1 + 1], z1 = vb[3 * i1 + 2];
-    const float x2 = vb[3 * i2], y2 = vb[3 * i2 + 1], z2 = vb[3 * i2 + 2];
-    r.q0 = make_float4(x0, y0, z0, x1);
-    r.q1 = make_float4(y1, z1, x2, y2);
-    r.q2.x = z2;
-
-    // A face with a non-finite x or y can never win a pixel in the reference: its barycentric
-    // weights divide inf by inf (NaN depth), and NaN fails the z-test (DESIGN.md "Dropped faces").
-    bool alive = isfinite(x0) && isfinite(x1) && isfinite(x2) && isfinite(y0) && isfinite(y1) &&
-                 isfinite(y2);
-    // rasterize_cuda_kernel.cu:100-104, two rounded products
-    if (alive && !draw_backside) {
-        const float a = __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(x1, x0));
-        const float c = __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x2, x0));
-        if (a > c) alive = false;
-    }
-    // :118-121
-    if (alive) {
-        const float det = __fmaf_rn(x1, __fsub_rn(y2, y0),
-                                    __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
-        if ((double)fabsf(det) < 0.00000001) alive = false;
-    }
-    xlo = 1; xhi = 0; ylo = 1; yhi = 0;
-    if (alive) {
-        // :94-97  pixel passes iff  min <= centre <= max  on both axes
-        const PixGrid grid(R);
-        xlo = first_pixel_ge(fminf(x0, fminf(x1, x2)), grid);
-        xhi = last_pixel_le(fmaxf(x0, fmaxf(x1, x2)), grid);
-        ylo = first_pixel_ge(fminf(y0, fminf(y1, y2)), grid);
-        yhi = last_pixel_le(fmaxf(y0, fmaxf(y1, y2)), grid);
-        if (xlo > xhi || ylo > yhi) alive = false;
-    }
-    if (alive) {
-        r.q2.y = __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16));
-        r.q2.z = __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16));
-    }
-    return alive;
-}
-
 __global__ void __launch_bounds__(256)
 k_setup_count(const float *__restrict__ verts, const int32_t *__restrict__ faces, int B, int nv,
               int nf, int R, int draw_backside, FaceRec *__restrict__ rec,
@@ -717,10 +655,8 @@ cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream) {
             k_scatter<<<blocks, 256, 0, stream>>>(a.rec, a.B, a.nf, a.ntx, a.tile_shift, a.tile_cursor, a.pairs,
                                                   a.pair_capacity, a.hdr);
         }
-        if (!a.unsorted) {
-            ProfScope p(PROF_SORT_LONG, stream);
-            k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
-        }
+        ProfScope p(PROF_SORT_LONG, stream);
+        k_sort_tiles<<<a.sm_count * 8, SORT_WARPS * 32, 0, stream>>>(a.tile_list, a.B * nt, a.pairs, a.hdr);
 
     }
     return cudaGetLastError();

@@ -30,7 +30,12 @@ struct BinHeader {
     int overflow;
     int bad_index;
     int work_counter;   // dynamic tile scheduler of the persistent raster kernel
-    int pad[59];
+    // z-buffer path (nr_raster_zbuf.cu)
+    int zb_big;         // faces queued for the warp-per-face pass
+    int zb_slots;       // contested pixels
+    int zb_nodes;       // candidates collected for them
+    int zb_work[4];     // dynamic schedulers of its persistent kernels
+    int pad[52];
 };
 
 // Non-empty tiles of one forward call, consumed by the raster kernel and again by the backward.
@@ -104,6 +109,11 @@ struct PixGrid {
 // the two loops make the result exact for any guess (center() is strictly increasing in i).
 __device__ __forceinline__ int first_pixel_ge(float v, const PixGrid &g) {
     const int R = g.R;
+    if (g.pow2) {
+        // center(i) = (2i + 1 - R) / R exactly, and t = v * R is exact too: center(i) >= v  <=>  2i + 1 - R >= ceil(t)
+        const float t = fminf(fmaxf(__fmul_rn(v, (float)R), -2.f * (float)R), 2.f * (float)R);
+        return min(max((__float2int_ru(t) + R) >> 1, 0), R);
+    }
     const float t = fmaf(v, 0.5f * (float)R, 0.5f * (float)(R - 1));
     int i = (t > 0.f) ? ((t >= (float)R) ? R : (int)ceilf(t)) : 0;      // NaN -> 0
     while (i > 0 && g.center(i - 1) >= v) --i;
@@ -114,11 +124,78 @@ __device__ __forceinline__ int first_pixel_ge(float v, const PixGrid &g) {
 // largest i in [-1, R-1] with center(i) <= v   (-1 if none)
 __device__ __forceinline__ int last_pixel_le(float v, const PixGrid &g) {
     const int R = g.R;
+    if (g.pow2) {
+        // center(i) <= v  <=>  2i + 1 - R <= floor(t)
+        const float t = fminf(fmaxf(__fmul_rn(v, (float)R), -2.f * (float)R), 2.f * (float)R);
+        return min(max((__float2int_rd(t) + R - 1) >> 1, -1), R - 1);
+    }
     const float t = fmaf(v, 0.5f * (float)R, 0.5f * (float)(R - 1));
     int i = (t >= 0.f) ? ((t >= (float)(R - 1)) ? R - 1 : (int)floorf(t)) : -1;   // NaN -> -1
     while (i < R - 1 && g.center(i + 1) <= v) ++i;
     while (i >= 0 && g.center(i) > v) --i;
     return i;
+}
+
+// Record of face f of one view (vb = that view's vertices) and its exact pixel box; returns false for
+// a face no pixel can accept (its record then carries the dead box).
+__device__ __forceinline__ bool make_face_record(const float *__restrict__ vb, const int32_t *__restrict__ faces,
+                                                 int f, int nv, int R, int draw_backside, FaceRec &r, int &xlo,
+                                                 int &xhi, int &ylo, int &yhi, BinHeader *__restrict__ hdr) {
+    int i0, i1, i2;
+    if (faces) {
+        i0 = __ldg(faces + 3 * f + 0);
+        i1 = __ldg(faces + 3 * f + 1);
+        i2 = __ldg(faces + 3 * f + 2);
+    } else {
+        i0 = 3 * f;
+        i1 = i0 + 1;
+        i2 = i0 + 2;
+    }
+    r.q0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.q1 = r.q0;
+    r.q2 = make_float4(0.f, __uint_as_float(DEAD_BBOX), 0.f, 0.f);
+    if ((unsigned)i0 >= (unsigned)nv || (unsigned)i1 >= (unsigned)nv || (unsigned)i2 >= (unsigned)nv) {
+        atomicOr(&hdr->bad_index, 1);
+        return false;
+    }
+    const float x0 = vb[3 * i0], y0 = vb[3 * i0 + 1], z0 = vb[3 * i0 + 2];
+    const float x1 = vb[3 * i1], y1 = vb[3 * i1 + 1], z1 = vb[3 * i1 + 2];
+    const float x2 = vb[3 * i2], y2 = vb[3 * i2 + 1], z2 = vb[3 * i2 + 2];
+    r.q0 = make_float4(x0, y0, z0, x1);
+    r.q1 = make_float4(y1, z1, x2, y2);
+    r.q2.x = z2;
+
+    // A face with a non-finite x or y can never win a pixel in the reference: its barycentric
+    // weights divide inf by inf (NaN depth), and NaN fails the z-test (DESIGN.md "Dropped faces").
+    bool alive = isfinite(x0) && isfinite(x1) && isfinite(x2) && isfinite(y0) && isfinite(y1) &&
+                 isfinite(y2);
+    // rasterize_cuda_kernel.cu:100-104, two rounded products
+    if (alive && !draw_backside) {
+        const float a = __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(x1, x0));
+        const float c = __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x2, x0));
+        if (a > c) alive = false;
+    }
+    // :118-121
+    if (alive) {
+        const float det = __fmaf_rn(x1, __fsub_rn(y2, y0),
+                                    __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
+        if ((double)fabsf(det) < 0.00000001) alive = false;
+    }
+    xlo = 1; xhi = 0; ylo = 1; yhi = 0;
+    if (alive) {
+        // :94-97  pixel passes iff  min <= centre <= max  on both axes
+        const PixGrid grid(R);
+        xlo = first_pixel_ge(fminf(x0, fminf(x1, x2)), grid);
+        xhi = last_pixel_le(fmaxf(x0, fmaxf(x1, x2)), grid);
+        ylo = first_pixel_ge(fminf(y0, fminf(y1, y2)), grid);
+        yhi = last_pixel_le(fmaxf(y0, fmaxf(y1, y2)), grid);
+        if (xlo > xhi || ylo > yhi) alive = false;
+    }
+    if (alive) {
+        r.q2.y = __uint_as_float((uint32_t)xlo | ((uint32_t)xhi << 16));
+        r.q2.z = __uint_as_float((uint32_t)ylo | ((uint32_t)yhi << 16));
+    }
+    return alive;
 }
 
 // Raw (un-normalised) barycentric numerators, rasterize_cuda_kernel.cu:130-132 / :276-278.

@@ -10,8 +10,8 @@ constexpr int SMEM_SORT_CAP = 8192;
 
 // Brackets one launch with CUDA events while nr_profile_enable(1) is in force (nr_profile.cu).
 enum ProfSlot { PROF_MEMSET = 0, PROF_SETUP, PROF_SCAN, PROF_SCATTER, PROF_SORT_LONG, PROF_RASTER,
-                PROF_BACKWARD, PROF_DIFF_BACKWARD, PROF_WEIGHT_MAP, PROF_RASTER_DENSE, PROF_CAMERA_FORWARD,
-                PROF_CAMERA_BACKWARD };
+                PROF_BACKWARD, PROF_DIFF_BACKWARD, PROF_WEIGHT_MAP, PROF_ZB_FACES, PROF_CAMERA_FORWARD,
+                PROF_CAMERA_BACKWARD, PROF_ZB_RESOLVE, PROF_ZB_SHADE };
 class ProfScope {
 public:
     ProfScope(int slot, cudaStream_t stream);
@@ -35,8 +35,6 @@ struct BinningArgs {
     int sm_count;
     int one_cta_per_view;   // allow the single-kernel small-mesh path (k_bin_view)
     int tile_shift;         // log2 of the tile edge: 4 (16x16), or 3 (8x8, general path only); ntx counts these tiles
-    int unsorted;           // general path: leave the tile lists in scatter order (the dense raster kernel orders
-                            // the few candidates it needs itself)
 };
 bool binning_fits_one_cta_per_view(int nf, int R);
 cudaError_t launch_binning(const BinningArgs &a, cudaStream_t stream);
@@ -64,6 +62,16 @@ struct RasterArgs {
     LightArgs lights;
     int fine;               // 8x8 tiles (ntx and the tile list are in those units)
     int sparse_maps;        // fim / internal only where the backward reads them (see NR_SPARSE_MAPS)
+    // z-buffer path for meshes of small triangles (nr_raster_zbuf.cu); null / 0 otherwise
+    const float *verts;             // [B, nv, 3]
+    unsigned long long *zbuf;       // [B, R, R]  (bits of the cheap depth) << 32 | face
+    unsigned *zb_bitmap;            // [B, R, zb_wpr] contested pixels, right behind the header
+    unsigned *zb_coarse;            // [B, zb_crows, zb_wpr] OR of eight rows of it, right behind the bitmap
+    uint2 *zb_box;                  // [B, nf] exact pixel box of every face (x lo | hi << 16, y lo | hi << 16)
+    int zb_wpr, zb_crows;           // 32-bit words per row; ceil(R / 8)
+    int *zb_head, *zb_pix_of;       // [zb_slot_cap] candidate list head / pixel of every contested pixel
+    int4 *zb_nodes;                 // [zb_node_cap] (face, depth, min corner depth, next)
+    int zb_slot_cap, zb_node_cap;
     // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
     int num_zero;
     void *zero_ptr[4];
@@ -71,7 +79,7 @@ struct RasterArgs {
 };
 cudaError_t launch_background_fill(const RasterArgs &a, cudaStream_t stream);
 cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream);
-cudaError_t launch_raster_dense(const RasterArgs &a, cudaStream_t stream);     // nr_raster_dense.cu
+cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream);      // nr_raster_zbuf.cu
 
 struct BackwardArgs {
     const float *verts;     // [B, nv, 3]

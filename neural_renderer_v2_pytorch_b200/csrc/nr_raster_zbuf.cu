@@ -1,0 +1,729 @@
+// nr_raster_zbuf.cu -- rasterizer for meshes of SMALL triangles (a 100 k-face sphere at 512^2, a million random
+// triangles at 1024^2: hundreds of faces per 16x16 tile, a few pixels per face).
+//
+// There the tile pipeline (nr_binning.cu + nr_raster.cu) spends its time on the lists, not on pixels: tens of
+// millions of (tile, face) pairs to count, scatter and sort into ascending face order, and a raster kernel that
+// evaluates every face of a list for all 32 pixels of a warp block although the face covers a handful.  This
+// path has NO lists and NO per-face records.  It turns the loops around:
+//
+//   k_zb_faces    one THREAD per (view, face): gathers the 3 vertices (rasterize.py:232), applies the tests that
+//                 do not depend on the pixel (back-face :100-104, degenerate :118-121), finds the exact pixel box
+//                 (:94-97), walks its pixels, evaluates the reference's edge functions (:107-116) and, where the
+//                 pixel is covered, merges (cheap depth, face) into a 64-bit z-buffer in global memory with ONE
+//                 atomicMin.  A face whose box is larger than ZB_BIG_AREA pixels is walked by its whole warp.
+//   k_zb_slots    numbers the CONTESTED pixels (below) and hands each a list head.
+//   k_zb_collect  one thread per (view, face) again: for the contested pixels inside its box (a few bit tests
+//                 per row) the reference's own depth (:129-139) goes into that pixel's candidate list.
+//   k_zb_resolve  one warp per contested pixel: orders its candidates by face index and replays the
+//                 reference's sequential scan (:124-148) on them.
+//   k_zb_shade    one CTA per 16x16 tile: winner -> weight map, texture sample, lights, silhouette, depth,
+//                 flip, anti-aliasing (shade_block, nr_shade.cuh), and the backward's list of non-empty tiles.
+//
+// Why the minimum is enough.  The reference's z-test is a SEQUENTIAL scan with a 1e-4 hysteresis (:145-148), not
+// a minimum.  But a candidate is only ever replaced by one at least delta closer, and the closest one is accepted
+// whenever it arrives: for a pixel whose closest candidate is closer than every other by more than the
+// hysteresis (plus the error bound of the cheap depth), the scan ends on that candidate whatever the order.
+// atomicMin returns the minimum of the moment; a candidate that comes within the band of it marks the pixel
+// contested (of two near candidates the later one always sees the earlier one or something closer still, so no
+// near-tie with the FINAL minimum is missed), and so does everything irregular: weights of mixed sign (the
+// c2 == 0 quirk of :109,114), depths that are not ordinary positive numbers, a depth within the error bound of
+// near or far.  Contested pixels - a fraction of a percent - are decided by the exact replay.  face_index_map is
+// bit-identical to the tile pipeline's and to the reference's (tests: every parity case runs through both).
+//
+// If the candidate pool overflows (nrBinStats.overflow; the host grows it for the next call) the lists are
+// unusable and every contested pixel is decided by the reference's own loop over ALL faces of its view, one warp
+// per pixel: slow, exact.
+#include "nr_shade.cuh"
+
+namespace nr {
+
+constexpr unsigned long long ZB_EMPTY = ~0ull;
+constexpr int ZB_CAND = 128;        // candidates of one contested pixel sorted in shared memory (more: loop over all faces)
+constexpr int ZB_THREADS = 256;
+
+// Everything the per-pixel tests need of one face, in registers.
+struct ZbFace {
+    float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+    float dx10, dy10, dx21, dy21, dx02, dy02;       // x1-x0, y1-y0, x2-x1, y2-y1, x0-x2, y0-y2 (rounded once, like :107-116)
+    float k0, k1, k2;                               // the pixel-independent half of the raw weights (:130-132)
+    float iz0, iz1, iz2;
+    bool zreg;
+    int fid;
+};
+
+__device__ __forceinline__ void zb_face_from_record(const FaceRec &r, int fid, ZbFace &f) {
+    f.x0 = r.q0.x; f.y0 = r.q0.y; f.z0 = r.q0.z; f.x1 = r.q0.w;
+    f.y1 = r.q1.x; f.z1 = r.q1.y; f.x2 = r.q1.z; f.y2 = r.q1.w; f.z2 = r.q2.x;
+    f.dx10 = __fsub_rn(f.x1, f.x0); f.dy10 = __fsub_rn(f.y1, f.y0);
+    f.dx21 = __fsub_rn(f.x2, f.x1); f.dy21 = __fsub_rn(f.y2, f.y1);
+    f.dx02 = __fsub_rn(f.x0, f.x2); f.dy02 = __fsub_rn(f.y0, f.y2);
+    f.k0 = __fmaf_rn(f.x1, f.y2, -__fmul_rn(f.x2, f.y1));
+    f.k1 = __fmaf_rn(f.x2, f.y0, -__fmul_rn(f.x0, f.y2));
+    f.k2 = __fmaf_rn(f.x0, f.y1, -__fmul_rn(f.x1, f.y0));
+    f.zreg = face_z_regular(f.z0, f.z1, f.z2);
+    f.iz0 = fast_rcp(f.z0); f.iz1 = fast_rcp(f.z1); f.iz2 = fast_rcp(f.z2);
+    f.fid = fid;
+}
+
+// :107-116.  rn(a - b) == -rn(b - a), so the deltas above give the reference's bits.
+__device__ __forceinline__ bool zb_inside(const ZbFace &f, float xp, float yp) {
+    const float c1 = __fmaf_rn(__fsub_rn(yp, f.y0), f.dx10, -__fmul_rn(f.dy10, __fsub_rn(xp, f.x0)));
+    const float c2 = __fmaf_rn(__fsub_rn(yp, f.y1), f.dx21, -__fmul_rn(f.dy21, __fsub_rn(xp, f.x1)));
+    const float c3 = __fmaf_rn(__fsub_rn(yp, f.y2), f.dx02, -__fmul_rn(f.dy02, __fsub_rn(xp, f.x2)));
+    return !((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f));
+}
+
+// raw_weights() (nr_common.cuh) from the precomputed halves: same operations, same bits
+__device__ __forceinline__ void zb_weights(const ZbFace &f, float xp, float yp, float &w0, float &w1, float &w2) {
+    w0 = __fadd_rn(__fmaf_rn(yp, f.dx21, __fmul_rn(xp, -f.dy21)), f.k0);
+    w1 = __fadd_rn(__fmaf_rn(yp, f.dx02, __fmul_rn(xp, -f.dy02)), f.k1);
+    w2 = __fadd_rn(__fmaf_rn(yp, f.dx10, __fmul_rn(xp, -f.dy10)), f.k2);
+}
+
+__device__ __forceinline__ void zb_flag(const RasterArgs &a, int b, int x, int y) {
+    atomicOr(a.zb_bitmap + ((size_t)b * a.R + y) * a.zb_wpr + (x >> 5), 1u << (x & 31));
+}
+
+// One (face, pixel) candidate that passed the inside test, first half: its cheap depth.  Returns true when that
+// depth goes into the z-buffer (zb_commit); an irregular candidate marks its pixel contested here, one that
+// can never win is dropped.
+__device__ __forceinline__ bool zb_prepare(const RasterArgs &a, const ZbFace &f, float xp, float yp, int b, int x, int y, float &zf) {
+    float w0, w1, w2;
+    zb_weights(f, xp, yp, w0, w1, w2);
+    if (!(f.zreg && weights_one_sign(w0, w1, w2))) {
+        zb_flag(a, b, x, y);                // irregular: the exact scan decides this pixel
+        return false;
+    }
+    zf = fast_zp(w0, w1, w2, f.iz0, f.iz1, f.iz2);
+    const float m = FAST_Z_REL * zf;
+    // :140-142 rejects zp <= near and zp >= far; a depth in (far - delta, far) is valid but can never pass the
+    // z-test against the initial minimum `far`, nor against a smaller one: it is irrelevant as well
+    const float top = a.far_plane - a.delta;
+    if (zf < a.near_plane - m || zf > top + m) return false;
+    // (a NaN fails every comparison above and the one below: contested)
+    if (!(zf > a.near_plane + m && zf < top - m && zf * 1e-6f < a.delta)) {
+        zb_flag(a, b, x, y);
+        return false;
+    }
+    return true;
+}
+// ... second half, after the atomicMin returned the minimum of the moment (`old`)
+__device__ __forceinline__ void zb_check(const RasterArgs &a, float zf, unsigned long long old, int b, int x, int y) {
+    if (old == ZB_EMPTY) return;
+    const float zo = __uint_as_float((unsigned)(old >> 32));
+    // within the hysteresis (plus both error bounds and the rounding of depth_min - delta) of the minimum of
+    // this moment: order may matter
+    if (fabsf(zf - zo) < a.delta + 2.5f * FAST_Z_REL * fmaxf(zf, zo)) zb_flag(a, b, x, y);
+}
+__device__ __forceinline__ unsigned long long zb_key(float zf, int fid) {
+    return ((unsigned long long)__float_as_uint(zf) << 32) | (unsigned)fid;
+}
+
+// Face f of view b: record + exact pixel box; false when no pixel can accept it.
+__device__ __forceinline__ bool zb_setup(const RasterArgs &a, int b, int f, ZbFace &F, int &xlo, int &xhi, int &ylo, int &yhi) {
+    FaceRec r;
+    const bool alive = make_face_record(a.verts + (size_t)b * a.nv * 3, a.faces, f, a.nv, a.R, (a.flags & FLAG_BACKSIDE) ? 1 : 0,
+                                        r, xlo, xhi, ylo, yhi, a.hdr);
+    if (alive) zb_face_from_record(r, f, F);
+    return alive;
+}
+
+// ---------------------------------------------------------------------------------------------- pass 1
+// A CTA owns 256 consecutive (view, face) pairs.  Their pixel boxes differ wildly (1 .. hundreds of pixels), so
+// "one thread walks its own face" leaves most lanes idle; instead the boxes of the CTA are laid end to end
+// (prefix sum of their areas in shared memory) and every thread tests the SAME number of consecutive
+// (face, pixel) items, ZB_ROUND per round.  The items that pass the inside test are compacted into a
+// shared-memory queue (one ballot + one shared atomic per warp and item), and the queue is then drained four
+// entries per thread at a time: four cheap depths, four atomicMin issued back to back, then the four checks.
+// The atomicMin has to RETURN the old minimum, a round trip to L2 of about a microsecond under load: the
+// kernel lives on how many of them it keeps in flight.
+constexpr int ZB_ROUND = 16;        // items per thread and round
+constexpr int ZB_HUGE = 4096;       // larger pixel boxes (r, c no longer fit 12 bits) are walked by a whole warp, unqueued
+
+struct ZbFacesShared {
+    // of the CTA's faces: v = x0 y0 x1 y1 x2 y2 | dx10 dy10 dx21 dy21 dx02 dy02 | k0 k1 k2 | iz0 iz1 iz2 (ZbFace);
+    float v[18][ZB_THREADS];
+    int box[ZB_THREADS];            // xlo | ylo << 16
+    int wh[ZB_THREADS];             // width | height << 16 of the pixel box
+    int irregular[ZB_THREADS];      // depths that are not ordinary positive numbers (face_z_regular)
+    int fid[ZB_THREADS], view[ZB_THREADS];
+    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the areas (dead and huge faces count 0)
+    unsigned hits[ZB_THREADS / 32][32 * ZB_ROUND];      // per warp: face (local) << 24 | row << 12 | column, inside the box
+    int wsum[ZB_THREADS / 32];
+};
+
+// the part of ZbFace the depth of a covered pixel needs (zb_prepare)
+__device__ __forceinline__ void zb_face_from_shared(const ZbFacesShared &sh, int i, ZbFace &f) {
+    f.dx10 = sh.v[6][i]; f.dy10 = sh.v[7][i]; f.dx21 = sh.v[8][i]; f.dy21 = sh.v[9][i]; f.dx02 = sh.v[10][i]; f.dy02 = sh.v[11][i];
+    f.k0 = sh.v[12][i]; f.k1 = sh.v[13][i]; f.k2 = sh.v[14][i];
+    f.iz0 = sh.v[15][i]; f.iz1 = sh.v[16][i]; f.iz2 = sh.v[17][i];
+    f.zreg = sh.irregular[i] == 0;
+    f.fid = sh.fid[i];
+}
+// ... and the whole of it (huge faces)
+__device__ __forceinline__ void zb_whole_face_from_shared(const ZbFacesShared &sh, int i, ZbFace &f) {
+    zb_face_from_shared(sh, i, f);
+    f.x0 = sh.v[0][i]; f.y0 = sh.v[1][i]; f.x1 = sh.v[2][i]; f.y1 = sh.v[3][i]; f.x2 = sh.v[4][i]; f.y2 = sh.v[5][i];
+    f.z0 = f.z1 = f.z2 = 0.f;       // (the cheap depth uses the reciprocals)
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(ZB_THREADS)
+k_zb_faces(const RasterArgs a) {
+    __shared__ ZbFacesShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int R = a.R;
+    const PixGrid grid(R);
+    auto center = [&](int i) -> float { return POW2 ? __fmul_rn((float)(2 * i + 1 - R), grid.invR) : pix_center(i, R); };
+    const long long idx = (long long)blockIdx.x * ZB_THREADS + tid;
+    const bool in = idx < (long long)a.B * a.nf;
+    const int b = in ? (int)(idx / a.nf) : 0, f = in ? (int)(idx % a.nf) : 0;
+    // ---- per-face setup (rasterize.py:232, :94-104, :118-121)
+    int area = 0;
+    bool huge = false;
+    {
+        FaceRec r;
+        int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+        const bool alive = in && make_face_record(a.verts + (size_t)b * a.nv * 3, a.faces, f, a.nv, R, (a.flags & FLAG_BACKSIDE) ? 1 : 0,
+                                                  r, xlo, xhi, ylo, yhi, a.hdr);
+        const int w = xhi - xlo + 1, h = yhi - ylo + 1;
+        if (alive) area = w * h;
+        huge = area > ZB_HUGE;
+        // the exact pixel box for the collect pass, which then needs no vertices for faces that touch nothing contested
+        if (in) a.zb_box[idx] = alive ? make_uint2((unsigned)xlo | ((unsigned)xhi << 16), (unsigned)ylo | ((unsigned)yhi << 16))
+                                      : make_uint2(DEAD_BBOX, 0u);
+        ZbFace F;
+        zb_face_from_record(r, f, F);
+        sh.v[0][tid] = F.x0; sh.v[1][tid] = F.y0; sh.v[2][tid] = F.x1; sh.v[3][tid] = F.y1; sh.v[4][tid] = F.x2; sh.v[5][tid] = F.y2;
+        sh.v[6][tid] = F.dx10; sh.v[7][tid] = F.dy10; sh.v[8][tid] = F.dx21; sh.v[9][tid] = F.dy21; sh.v[10][tid] = F.dx02; sh.v[11][tid] = F.dy02;
+        sh.v[12][tid] = F.k0; sh.v[13][tid] = F.k1; sh.v[14][tid] = F.k2;
+        sh.v[15][tid] = F.iz0; sh.v[16][tid] = F.iz1; sh.v[17][tid] = F.iz2;
+        sh.box[tid] = alive ? (xlo | (ylo << 16)) : 0;
+        sh.wh[tid] = alive ? (w | (h << 16)) : 0;
+        sh.irregular[tid] = F.zreg ? 0 : 1;
+        sh.fid[tid] = f;
+        sh.view[tid] = b;
+    }
+    // ---- the boxes end to end
+    {
+        const int my = huge ? 0 : area;
+        int inc = my;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sh.wsum[wid] = inc;
+        __syncthreads();
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < ZB_THREADS / 32; ++k)
+            if (k < wid) base += sh.wsum[k];
+        sh.pre[tid] = base + inc - my;
+        if (tid == ZB_THREADS - 1) sh.pre[ZB_THREADS] = base + inc;
+        __syncthreads();
+    }
+    const int W = sh.pre[ZB_THREADS];
+    const int chunk = (W + ZB_THREADS - 1) / ZB_THREADS;
+    int pos = min(tid * chunk, W);
+    const int end = min(pos + chunk, W);
+    // ---- my first item: face i = the one with pre[i] <= pos < pre[i + 1], then row and column inside its box
+    int i = 0, r = 0, c = 0, nxt = 0, fw = 1, fx = 0, fy = 0;
+    float x0 = 0.f, y0 = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, dx10 = 0.f, dy10 = 0.f, dx21 = 0.f, dy21 = 0.f, dx02 = 0.f, dy02 = 0.f;
+    auto load_face = [&](int j) {
+        x0 = sh.v[0][j]; y0 = sh.v[1][j]; x1 = sh.v[2][j]; y1 = sh.v[3][j]; x2 = sh.v[4][j]; y2 = sh.v[5][j];
+        dx10 = sh.v[6][j]; dy10 = sh.v[7][j]; dx21 = sh.v[8][j]; dy21 = sh.v[9][j]; dx02 = sh.v[10][j]; dy02 = sh.v[11][j];
+        fw = sh.wh[j] & 0xffff;
+        fx = sh.box[j] & 0xffff;
+        fy = (int)((unsigned)sh.box[j] >> 16);
+        nxt = sh.pre[j + 1];
+    };
+    if (pos < end) {
+        int lo = 0, hi = ZB_THREADS;            // first j with pre[j] > pos (pre[256] = W > pos)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sh.pre[mid] > pos) hi = mid; else lo = mid + 1;
+        }
+        i = lo - 1;
+        load_face(i);
+        const int k = pos - sh.pre[i];
+        r = k / fw;
+        c = k - r * fw;
+    }
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // The warps run on their own from here: the items of a warp's 32 threads go through the warp's own queue.
+    unsigned *queue = sh.hits[wid];
+    const int rounds = (wid * 32 * chunk < W) ? (chunk + ZB_ROUND - 1) / ZB_ROUND : 0;
+    for (int round = 0; round < rounds; ++round) {
+        // (a round: ZB_ROUND items of every thread of the warp)
+        // ---- phase A: inside tests (:107-116), hits into the queue
+        int H = 0;                                             // warp-uniform
+#pragma unroll 1
+        for (int j = 0; j < ZB_ROUND; ++j) {
+            bool hit = false;
+            unsigned code = 0u;
+            if (pos < end) {
+                const float xp = center(fx + c), yp = center(fy + r);
+                const float c1 = __fmaf_rn(__fsub_rn(yp, y0), dx10, -__fmul_rn(dy10, __fsub_rn(xp, x0)));
+                const float c2 = __fmaf_rn(__fsub_rn(yp, y1), dx21, -__fmul_rn(dy21, __fsub_rn(xp, x1)));
+                const float c3 = __fmaf_rn(__fsub_rn(yp, y2), dx02, -__fmul_rn(dy02, __fsub_rn(xp, x2)));
+                hit = !((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f));
+                code = ((unsigned)i << 24) | ((unsigned)r << 12) | (unsigned)c;
+                ++pos;
+                if (++c == fw) {
+                    c = 0;
+                    ++r;
+                }
+                if (pos == nxt && pos < end) {
+                    do ++i; while (sh.pre[i + 1] == sh.pre[i]);       // (faces without items)
+                    load_face(i);
+                    r = 0;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (hit) queue[H + __popc(m & lt_mask)] = code;
+            H += __popc(m);
+        }
+        __syncwarp();
+        // ---- phase B: the queue, four entries per lane at a time
+        for (int hb = 0; hb < H; hb += 4 * 32) {
+            float zf[4];
+            int pxy[4], fv[4], bv[4];
+            bool go[4];
+            unsigned long long old[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int h = hb + k * 32 + lane;
+                go[k] = false;
+                if (h < H) {
+                    const unsigned code = queue[h];
+                    const int li = code >> 24;
+                    ZbFace F;
+                    zb_face_from_shared(sh, li, F);
+                    const int x = (sh.box[li] & 0xffff) + (int)(code & 0xfff), y = (int)((unsigned)sh.box[li] >> 16) + (int)((code >> 12) & 0xfff);
+                    bv[k] = sh.view[li];
+                    fv[k] = F.fid;
+                    pxy[k] = x | (y << 16);
+                    go[k] = zb_prepare(a, F, center(x), center(y), bv[k], x, y, zf[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (go[k]) old[k] = atomicMin(a.zbuf + ((size_t)bv[k] * R + (pxy[k] >> 16)) * R + (pxy[k] & 0xffff), zb_key(zf[k], fv[k]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (go[k]) zb_check(a, zf[k], old[k], bv[k], pxy[k] & 0xffff, pxy[k] >> 16);
+        }
+        __syncwarp();
+    }
+    // ---- huge faces: the whole warp walks the box of one of its lanes' faces, a lane per pixel: the lanes form
+    // a (32 / wb) x wb patch, wb = the box width rounded up to a power of two (32 at most), that steps over the
+    // box; two patches per round keep two atomics per lane in flight
+    unsigned todo = __ballot_sync(0xffffffffu, huge);
+    int nhuge = __popc(todo);
+    while (todo) {
+        const int src = (wid << 5) + __ffs(todo) - 1;
+        todo &= todo - 1;
+        ZbFace G;
+        zb_whole_face_from_shared(sh, src, G);
+        const int sb = sh.view[src], gx0 = sh.box[src] & 0xffff, gy0 = (int)((unsigned)sh.box[src] >> 16);
+        const int gw = sh.wh[src] & 0xffff, gx1 = gx0 + gw - 1, gy1 = gy0 + (int)((unsigned)sh.wh[src] >> 16) - 1;
+        int shf = 0;
+        while ((1 << shf) < gw && shf < 5) ++shf;
+        const int wb = 1 << shf, rows = 32 >> shf, lc = lane & (wb - 1), lr = lane >> shf;
+        unsigned long long *zb = a.zbuf + (size_t)sb * R * R;
+        for (int yb = gy0; yb <= gy1; yb += 2 * rows) {
+            for (int xb = gx0; xb <= gx1; xb += wb) {
+                const int x = xb + lc;
+                float zf[2];
+                int py[2];
+                bool go[2];
+                unsigned long long old[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    py[k] = yb + k * rows + lr;
+                    go[k] = false;
+                    if (x <= gx1 && py[k] <= gy1) {
+                        const float xp = center(x), yp = center(py[k]);
+                        if (zb_inside(G, xp, yp)) go[k] = zb_prepare(a, G, xp, yp, sb, x, py[k], zf[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (go[k]) old[k] = atomicMin(zb + (size_t)py[k] * R + x, zb_key(zf[k], G.fid));
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (go[k]) zb_check(a, zf[k], old[k], sb, x, py[k]);
+            }
+        }
+    }
+    // statistics for the host: a mesh with many such faces belongs to the tile pipeline
+    if (nhuge && lane == 0) atomicAdd(&a.hdr->max_tile_faces, nhuge);
+}
+
+// ---------------------------------------------------------------------------------------------- pass 2
+// Every contested pixel gets a slot: its list head, and (in the face index map, which is not written before the
+// shade pass) the way from the pixel to the slot.
+__global__ void __launch_bounds__(ZB_THREADS)
+k_zb_slots(const RasterArgs a, long long words) {
+    const long long idx = (long long)blockIdx.x * ZB_THREADS + threadIdx.x;
+    if (idx == 0) {
+#pragma unroll
+        for (int k = 0; k < TILE_LIST_HDR; ++k) const_cast<int32_t *>(a.tile_list)[k] = 0;
+    }
+    if (idx >= words) return;
+    unsigned w = a.zb_bitmap[idx];
+    if (!w) return;
+    const int n = __popc(w);
+    int slot = atomicAdd(&a.hdr->zb_slots, n);
+    atomicAdd(&a.hdr->total_pairs, n);                    // reported to the host: contested pixels of this call
+    const long long row = idx / a.zb_wpr;                 // = b * R + y
+    const int xw = (int)(idx % a.zb_wpr) * 32;
+    {
+        // coarse bitmap: the OR of eight rows, so that the collect pass clears a face's box with a load or two
+        const int b = (int)(row / a.R), y = (int)(row % a.R);
+        atomicOr(a.zb_coarse + ((size_t)b * a.zb_crows + (y >> 3)) * a.zb_wpr + (idx % a.zb_wpr), w);
+    }
+    while (w) {
+        const int x = xw + __ffs(w) - 1;
+        w &= w - 1;
+        const long long pix = row * a.R + x;
+        if (slot < a.zb_slot_cap) {
+            a.zb_pix_of[slot] = (int)pix;
+            a.zb_head[slot] = -1;
+            a.fim[pix] = slot;
+        } else {
+            a.fim[pix] = 0x7fffffff;
+            a.hdr->overflow = 1;
+        }
+        ++slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pass 3
+// The reference's own depth of face F at a contested pixel -> the pixel's candidate list.
+__device__ __forceinline__ void zb_collect_pixel(const RasterArgs &a, const ZbFace &F, const PixGrid &grid, int b, int x, int y) {
+    const float xp = grid.center(x), yp = grid.center(y);
+    if (!zb_inside(F, xp, yp)) return;
+    float w0, w1, w2;
+    zb_weights(F, xp, yp, w0, w1, w2);
+    const float zp = exact_zp(w0, w1, w2, F.z0, F.z1, F.z2);
+    // :140-142; a NaN depth passes that test but then fails zp <= depth_min - delta: it never matters
+    if (zp <= a.near_plane || a.far_plane <= zp || zp != zp) return;
+    const int slot = a.fim[((size_t)b * a.R + y) * a.R + x];
+    if (slot >= a.zb_slot_cap) return;                   // no slot: the overflow path decides this pixel
+    const int node = atomicAdd(&a.hdr->zb_nodes, 1);
+    if (node >= a.zb_node_cap) {
+        a.hdr->overflow = 1;
+        return;
+    }
+    // the scan skips a face when depth_min < z0 && depth_min < z1 && depth_min < z2 (:124-126): with a NaN corner
+    // depth that is never true, otherwise it is depth_min < min(z)
+    const float zc = (F.z0 != F.z0 || F.z1 != F.z1 || F.z2 != F.z2) ? -__int_as_float(0x7f800000) : fminf(F.z0, fminf(F.z1, F.z2));
+    const int next = atomicExch(a.zb_head + slot, node);
+    a.zb_nodes[node] = make_int4(F.fid, __float_as_int(zp), __float_as_int(zc), next);
+}
+
+__global__ void __launch_bounds__(ZB_THREADS)
+k_zb_collect(const RasterArgs a) {
+    __shared__ int s_queue[ZB_THREADS];
+    __shared__ int s_n;
+    if (a.hdr->zb_slots == 0) return;                     // nothing contested (uniform over the grid)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long cta0 = (long long)blockIdx.x * ZB_THREADS, idx = cta0 + tid;
+    const PixGrid grid(a.R);
+    const bool in = idx < (long long)a.B * a.nf;
+    const int b = in ? (int)(idx / a.nf) : 0;
+    // the face's pixel box as pass 1 found it
+    int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+    if (in) {
+        const uint2 box = __ldg(a.zb_box + idx);
+        xlo = (int)(box.x & 0xffff); xhi = (int)(box.x >> 16); ylo = (int)(box.y & 0xffff); yhi = (int)(box.y >> 16);
+    }
+    const bool alive = in && xlo <= xhi;
+    // bits of columns [c0, c1] in bitmap word wq
+    auto col_mask = [](int wq, int c0, int c1) -> unsigned {
+        const int lo = max(c0 - wq * 32, 0), hi = min(c1 - wq * 32, 31);
+        return (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+    };
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const bool huge = alive && (xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE;
+    if (alive && !huge) {
+        // coarse test: most faces touch no contested pixel; the few that do are queued, so that the costly part
+        // (vertices, exact depths) runs on full warps
+        bool any = false;
+        for (int cy = ylo >> 3; cy <= (yhi >> 3); ++cy)
+            for (int wq = xlo >> 5; wq <= (xhi >> 5); ++wq)
+                any |= (__ldg(a.zb_coarse + ((size_t)b * a.zb_crows + cy) * a.zb_wpr + wq) & col_mask(wq, xlo, xhi)) != 0u;
+        if (any) s_queue[atomicAdd(&s_n, 1)] = tid;
+    }
+    __syncthreads();
+    if (tid < s_n) {
+        const long long qidx = cta0 + s_queue[tid];
+        const int qb = (int)(qidx / a.nf), qf = (int)(qidx % a.nf);
+        ZbFace F;
+        int qx0, qx1, qy0, qy1;
+        if (zb_setup(a, qb, qf, F, qx0, qx1, qy0, qy1)) {
+            for (int y = qy0; y <= qy1; ++y)
+                for (int wq = qx0 >> 5; wq <= (qx1 >> 5); ++wq) {
+                    unsigned bits = __ldg(a.zb_bitmap + ((size_t)qb * a.R + y) * a.zb_wpr + wq) & col_mask(wq, qx0, qx1);
+                    while (bits) {
+                        const int x = wq * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        zb_collect_pixel(a, F, grid, qb, x, y);
+                    }
+                }
+        }
+    }
+    // huge faces: the whole warp, a lane per (row, word)
+    unsigned todo = __ballot_sync(0xffffffffu, huge);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long sidx = __shfl_sync(0xffffffffu, idx, src);
+        const int sb = (int)(sidx / a.nf), sf = (int)(sidx % a.nf);
+        ZbFace G;
+        int gx0, gx1, gy0, gy1;
+        if (!zb_setup(a, sb, sf, G, gx0, gx1, gy0, gy1)) continue;
+        const int w0 = gx0 >> 5, nw = (gx1 >> 5) - w0 + 1;
+        const int items = nw * (gy1 - gy0 + 1);           // (row, word) pairs, a lane each
+        for (int k = lane; k < items; k += 32) {
+            const int y = gy0 + k / nw, wq = w0 + k % nw;
+            unsigned bits = __ldg(a.zb_bitmap + ((size_t)sb * a.R + y) * a.zb_wpr + wq) & col_mask(wq, gx0, gx1);
+            while (bits) {
+                const int x = wq * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                zb_collect_pixel(a, G, grid, sb, x, y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pass 4
+// The reference's loop (:82-149) for ONE pixel over all faces of its view, by a warp (overflow path, and pixels
+// with more candidates than ZB_CAND).  Returns the winning face or -1.
+__device__ __noinline__ int zb_scan_all_faces(const RasterArgs &a, int b, float xp, float yp, int lane) {
+    const float *vb = a.verts + (size_t)b * a.nv * 3;
+    const bool cull = !(a.flags & FLAG_BACKSIDE);
+    float depth_min = a.far_plane;
+    int best = -1;
+    for (int g = 0; g < a.nf; g += 32) {
+        const int f = g + lane;
+        float zp = 0.f, zc = 0.f;
+        bool keep = false;
+        if (f < a.nf) {
+            int i0 = 3 * f, i1 = 3 * f + 1, i2 = 3 * f + 2;
+            if (a.faces) { i0 = __ldg(a.faces + 3 * (size_t)f); i1 = __ldg(a.faces + 3 * (size_t)f + 1); i2 = __ldg(a.faces + 3 * (size_t)f + 2); }
+            if ((unsigned)i0 < (unsigned)a.nv && (unsigned)i1 < (unsigned)a.nv && (unsigned)i2 < (unsigned)a.nv) {
+                const float x0 = vb[3 * (size_t)i0], y0 = vb[3 * (size_t)i0 + 1], z0 = vb[3 * (size_t)i0 + 2];
+                const float x1 = vb[3 * (size_t)i1], y1 = vb[3 * (size_t)i1 + 1], z1 = vb[3 * (size_t)i1 + 2];
+                const float x2 = vb[3 * (size_t)i2], y2 = vb[3 * (size_t)i2 + 1], z2 = vb[3 * (size_t)i2 + 2];
+                // :94-97 (a NaN coordinate fails no comparison here but yields a NaN depth below)
+                keep = !(xp < fminf(x0, fminf(x1, x2)) || fmaxf(x0, fmaxf(x1, x2)) < xp || yp < fminf(y0, fminf(y1, y2)) ||
+                         fmaxf(y0, fmaxf(y1, y2)) < yp);
+                keep = keep && isfinite(x0) && isfinite(x1) && isfinite(x2) && isfinite(y0) && isfinite(y1) && isfinite(y2);
+                // :100-104
+                if (keep && cull && __fmul_rn(__fsub_rn(y2, y0), __fsub_rn(x1, x0)) > __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x2, x0))) keep = false;
+                if (keep) {
+                    // :107-116
+                    const float c1 = __fmaf_rn(__fsub_rn(yp, y0), __fsub_rn(x1, x0), -__fmul_rn(__fsub_rn(y1, y0), __fsub_rn(xp, x0)));
+                    const float c2 = __fmaf_rn(__fsub_rn(yp, y1), __fsub_rn(x2, x1), -__fmul_rn(__fsub_rn(y2, y1), __fsub_rn(xp, x1)));
+                    const float c3 = __fmaf_rn(__fsub_rn(yp, y2), __fsub_rn(x0, x2), -__fmul_rn(__fsub_rn(y0, y2), __fsub_rn(xp, x2)));
+                    keep = !((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f));
+                }
+                if (keep) {
+                    // :118-121
+                    const float det = __fmaf_rn(x1, __fsub_rn(y2, y0), __fmaf_rn(x2, __fsub_rn(y0, y1), __fmul_rn(x0, __fsub_rn(y1, y2))));
+                    keep = !((double)fabsf(det) < 0.00000001);
+                }
+                if (keep) {
+                    float w0, w1, w2;
+                    raw_weights(xp, yp, x0, y0, x1, y1, x2, y2, w0, w1, w2);
+                    zp = exact_zp(w0, w1, w2, z0, z1, z2);
+                    zc = (z0 != z0 || z1 != z1 || z2 != z2) ? -__int_as_float(0x7f800000) : fminf(z0, fminf(z1, z2));
+                    keep = !(zp <= a.near_plane || a.far_plane <= zp) && zp == zp;
+                }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, keep);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float szp = __shfl_sync(0xffffffffu, zp, src), szc = __shfl_sync(0xffffffffu, zc, src);
+            if (depth_min < szc) continue;                              // :124-126
+            if (szp <= __fsub_rn(depth_min, a.delta)) {                  // :145-148
+                depth_min = szp;
+                best = g + src;
+            }
+        }
+    }
+    return best;
+}
+
+struct ZbResolveShared {
+    int f[ZB_THREADS / 32][2][ZB_CAND];
+    float z[ZB_THREADS / 32][2][ZB_CAND];
+    float c[ZB_THREADS / 32][2][ZB_CAND];
+};
+
+__global__ void __launch_bounds__(ZB_THREADS)
+k_zb_resolve(const RasterArgs a, long long words) {
+    __shared__ ZbResolveShared sh;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const PixGrid grid(a.R);
+    const long long gw = (long long)blockIdx.x * (ZB_THREADS / 32) + wid, nwarps = (long long)gridDim.x * (ZB_THREADS / 32);
+    const long long plane = (long long)a.R * a.R;
+    auto put = [&](long long pix, int best) {
+        if (lane == 0) a.zbuf[pix] = best >= 0 ? (unsigned long long)(unsigned)best : ZB_EMPTY;
+    };
+    if (a.hdr->overflow) {
+        // lists unusable: every contested pixel by the loop over all faces
+        for (long long wi = gw; wi < words; wi += nwarps) {
+            unsigned bits = a.zb_bitmap[wi];
+            const long long row = wi / a.zb_wpr;
+            const int xw = (int)(wi % a.zb_wpr) * 32, b = (int)(row / a.R), y = (int)(row % a.R);
+            while (bits) {
+                const int x = xw + __ffs(bits) - 1;
+                bits &= bits - 1;
+                put(row * a.R + x, zb_scan_all_faces(a, b, grid.center(x), grid.center(y), lane));
+            }
+        }
+        return;
+    }
+    const int slots = min(a.hdr->zb_slots, a.zb_slot_cap);
+    int *cf = sh.f[wid][0], *sf = sh.f[wid][1];
+    float *cz = sh.z[wid][0], *sz = sh.z[wid][1], *cc = sh.c[wid][0], *sc = sh.c[wid][1];
+    for (long long slot = gw; slot < slots; slot += nwarps) {
+        const long long pix = a.zb_pix_of[slot];
+        // ---- the list into shared memory (lane 0 walks it)
+        int count = 0;
+        if (lane == 0) {
+            for (int node = a.zb_head[slot]; node >= 0;) {
+                const int4 nd = a.zb_nodes[node];
+                if (count < ZB_CAND) {
+                    cf[count] = nd.x;
+                    cz[count] = __int_as_float(nd.y);
+                    cc[count] = __int_as_float(nd.z);
+                }
+                ++count;
+                node = nd.w;
+            }
+        }
+        count = __shfl_sync(0xffffffffu, count, 0);
+        __syncwarp();
+        if (count > ZB_CAND) {
+            const int b = (int)(pix / plane), rem = (int)(pix % plane);
+            put(pix, zb_scan_all_faces(a, b, grid.center(rem % a.R), grid.center(rem / a.R), lane));
+            continue;
+        }
+        // ---- order by face index (rank = number of smaller ids; ids are distinct), then the reference's scan
+        for (int i = lane; i < count; i += 32) {
+            const int fi = cf[i];
+            int r = 0;
+            for (int j = 0; j < count; ++j) r += cf[j] < fi;
+            sf[r] = fi;
+            sz[r] = cz[i];
+            sc[r] = cc[i];
+        }
+        __syncwarp();
+        float depth_min = a.far_plane;
+        int best = -1;
+        if (lane == 0) {
+            for (int j = 0; j < count; ++j) {
+                const float zp = sz[j];
+                if (depth_min < sc[j]) continue;                         // :124-126
+                if (zp <= __fsub_rn(depth_min, a.delta)) {                // :145-148
+                    depth_min = zp;
+                    best = sf[j];
+                }
+            }
+        }
+        put(pix, best);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pass 5
+template <bool RGB, bool AA, bool FULL>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_zb_shade(const RasterArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int R = a.R;
+    const PixGrid grid(R);
+    const bool has_bg = FULL && RGB && a.lights.backgrounds != nullptr;
+    // the caller's zero buffers (gradient accumulators of the coming backward) ride along: stores only
+    const FillPlan plan = make_fill_plan(a);
+    for (int fi = plan.all_tiles + blockIdx.x * (TILE_THREADS / 32) + wid; fi < plan.fill_items; fi += gridDim.x * (TILE_THREADS / 32))
+        do_fill_item<AA, FULL, false>(a, plan, fi, lane);
+
+    const int nt = a.ntx * a.ntx;
+    const int b = blockIdx.x / nt, t = blockIdx.x % nt, ty = t / a.ntx, tx = t % a.ntx;
+    int px, py;
+    tile_pixel(tid, px, py);
+    const int xi = tx * TILE + px, yi = ty * TILE + py;
+    const bool valid = xi < R && yi < R;
+    int best = -1;
+    if (valid) {
+        const unsigned long long key = a.zbuf[((size_t)b * R + yi) * R + xi];
+        if (key != ZB_EMPTY) best = (int)(unsigned)(key & 0xffffffffu);
+    }
+    float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
+    if (best >= 0) {
+        int i0 = 3 * best, i1 = 3 * best + 1, i2 = 3 * best + 2;
+        if (a.faces) { i0 = __ldg(a.faces + 3 * (size_t)best); i1 = __ldg(a.faces + 3 * (size_t)best + 1); i2 = __ldg(a.faces + 3 * (size_t)best + 2); }
+        const float *vb = a.verts + (size_t)b * a.nv * 3;
+        const float x0 = __ldg(vb + 3 * (size_t)i0), y0 = __ldg(vb + 3 * (size_t)i0 + 1);
+        const float x1 = __ldg(vb + 3 * (size_t)i1), y1 = __ldg(vb + 3 * (size_t)i1 + 1);
+        const float x2 = __ldg(vb + 3 * (size_t)i2), y2 = __ldg(vb + 3 * (size_t)i2 + 1);
+        bz0 = __ldg(vb + 3 * (size_t)i0 + 2); bz1 = __ldg(vb + 3 * (size_t)i1 + 2); bz2 = __ldg(vb + 3 * (size_t)i2 + 2);
+        raw_weights(grid.center(xi), grid.center(yi), x0, y0, x1, y1, x2, y2, bw0, bw1, bw2);
+    }
+    shade_block<RGB, AA, FULL>(a, b, xi, yi, valid, best, bw0, bw1, bw2, bz0, bz1, bz2, has_bg);
+    // the backward walks the non-empty tiles only
+    const int any = __syncthreads_or(best >= 0);
+    if (any && tid == 0) {
+        int32_t *tl = const_cast<int32_t *>(a.tile_list);
+        const int i = atomicAdd(tl, 1);           // all in class 0
+        reinterpret_cast<int4 *>(tl + TILE_LIST_HDR)[i] = make_int4(b, tx | (ty << 16), 0, 0);
+    }
+}
+
+cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
+    if (a.B <= 0 || a.R <= 0) return cudaSuccess;
+    const long long faces = (long long)a.B * a.nf, words = (long long)a.B * a.R * a.zb_wpr;
+    const long long plane = (long long)a.B * a.R * a.R;
+    cudaError_t e;
+    {
+        ProfScope p(PROF_MEMSET, stream);
+        // header, bitmap and coarse bitmap are adjacent
+        const size_t coarse_words = (size_t)a.B * a.zb_crows * a.zb_wpr;
+        if ((e = cudaMemsetAsync(a.hdr, 0, sizeof(BinHeader) + ((size_t)words + coarse_words) * sizeof(unsigned), stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.zbuf, 0xff, (size_t)plane * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    }
+    const unsigned face_ctas = (unsigned)((faces + ZB_THREADS - 1) / ZB_THREADS);
+    if (face_ctas) {
+        ProfScope p(PROF_ZB_FACES, stream);
+        if ((a.R & (a.R - 1)) == 0) k_zb_faces<true><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+        else k_zb_faces<false><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+    }
+    {
+        ProfScope p(PROF_ZB_RESOLVE, stream);
+        k_zb_slots<<<(unsigned)((words + ZB_THREADS - 1) / ZB_THREADS), ZB_THREADS, 0, stream>>>(a, words);
+        if (face_ctas) k_zb_collect<<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+        k_zb_resolve<<<a.sm_count * 4, ZB_THREADS, 0, stream>>>(a, words);
+    }
+    const bool rgb = (a.flags & FLAG_RGB) != 0, aa = (a.flags & FLAG_AA) != 0;
+    const bool full = a.lights.num > 0 || a.lights.backgrounds || a.wmap || a.dmap || !a.images || (a.R & 15);
+    const unsigned tiles = (unsigned)((long long)a.B * a.ntx * a.ntx);
+    ProfScope p(PROF_ZB_SHADE, stream);
+    // silhouettes of dense meshes are the measured case; everything else takes the full-featured variants
+    if (!rgb && !aa && !full) k_zb_shade<false, false, false><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    else if (rgb && aa) k_zb_shade<true, true, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    else if (rgb) k_zb_shade<true, false, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    else if (aa) k_zb_shade<false, true, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    else k_zb_shade<false, false, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace nr

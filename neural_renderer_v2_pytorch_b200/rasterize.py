@@ -87,8 +87,11 @@ class _Scratch:
         self.overflows = 0
         self.general_binning = set()        # (nf, R) whose views outgrew the one-kernel small-mesh binning
         self.fine_tiles = set()             # (nf, R) dense enough for 8x8 tiles (general path only)
-        self.dense = set()                  # (nf, R) of small triangles: face-parallel raster kernel
+        self.dense = set()                  # (nf, R) of small triangles: face-parallel z-buffer rasterizer
+        self.not_dense = set()              # ... that turned out to hold too many large faces for it
+        self.last_dense = False
         self.last_tiles = 1
+        self.last_faces = 0
         self.bad_index = 0                  # nrBinStats.bad_index bits seen and not yet reported
         self.last_shape = None
         self.last_small = True
@@ -115,15 +118,25 @@ class _Scratch:
             return
         self.pending = False
         total, max_tile, overflow, bad = self.stats.tolist()
-        if self.last_shape is not None and not self.last_small:
+        if self.last_dense:
+            # z-buffer path: total = contested pixels, max_tile = faces with a pixel box above 4096 pixels
+            if max_tile * 50 > self.last_faces and self.last_shape is not None:
+                self.dense.discard(self.last_shape)
+                self.not_dense.add(self.last_shape)
+        elif self.last_shape is not None and not self.last_small:
             if max_tile > FINE_TILES_ABOVE:
                 self.fine_tiles.add(self.last_shape)
-            if total >= DENSE_RASTER_ABOVE * self.last_tiles:
+            # many faces per tile, few tiles per face: small triangles
+            if (total >= DENSE_RASTER_ABOVE * self.last_tiles and total <= 3 * self.last_faces
+                    and self.last_shape not in self.not_dense):
                 self.dense.add(self.last_shape)
         self.bad_index |= bad
         if overflow:
             self.overflows += 1
-            self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
+            if self.last_dense:
+                self.pair_capacity = min(max(self.pair_capacity * 4, 1 << 20), 0x7fffffff)
+            else:
+                self.pair_capacity = max(self.pair_capacity, int(total * 1.25) + 4096)
             if overflow == 2:
                 self.general_binning.add(self.last_shape)
 
@@ -254,6 +267,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
             cfg.flags |= _lib.NR_SPARSE_MAPS     # fim / internal image are only handed to the backward
         if track:
             sc.last_shape, sc.last_small, sc.last_tiles = shape, small, B * ((R + 15) // 16) ** 2
+            sc.last_dense, sc.last_faces = dense, B * cfg.num_faces
         if capturing and _capture_keepalive is not None:
             _capture_keepalive.append(ws)
         rc = L.nr_rasterize_forward(
