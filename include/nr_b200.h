@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 3
+#define NR_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NR_API __attribute__((visibility("default")))
@@ -194,6 +194,12 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
  *   images_internal     [B, C, R, R] out, required with NR_ANTI_ALIASING (the backward
  *                                    stencil runs at internal resolution), else may be NULL
  *                                    (then `images` itself is the internal image)
+ *   aux_map             [B, R, R, 6] with NR_DRAW_RGB, else [B, R, R, 3]: out, optional (NULL to skip), 8-byte
+ *                       aligned.  Forward -> backward state, written at FOREGROUND pixels only (not initialised
+ *                       elsewhere): the normalised weights w0 w1 w2 and, with colour, the three quotients of the
+ *                       perspective-correct texel coordinate (rasterize.py:113-119: depth, sum w u / z, sum w v / z).
+ *                       Handed to nr_rasterize_backward it saves that kernel 9 scattered vertex loads and 12 IEEE
+ *                       divisions per pixel (the forward has the values in registers anyway).
  *   tile_list           [8 + 16 * B * ceil(R/16)^2] i32 out, optional, 16-byte aligned: the non-empty
  *                       16x16 tiles in four length classes (longest face lists first); elements 0..3
  *                       = entries per class, then 4 ints per tile (view, tile_x | tile_y << 16, list
@@ -212,8 +218,8 @@ NR_API size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacit
 NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,
                          const float *textures, int32_t *face_index_map, float *weight_map,
-                         float *depth_map, float *images, float *images_internal, int32_t *tile_list,
-                         void *workspace, size_t workspace_bytes, int64_t pair_capacity,
+                         float *depth_map, float *images, float *images_internal, float *aux_map,
+                         int32_t *tile_list, void *workspace, size_t workspace_bytes, int64_t pair_capacity,
                          nrBinStats *stats_host, void *stats_event, const nrZeroFill *zero_fill,
                          const nrLights *lights, void *stream);
 
@@ -225,6 +231,8 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
  *
  *   face_index_map      [B, R, R]    from the forward
  *   images_internal     [B, C, R, R] from the forward (pass `images` when not anti-aliased)
+ *   aux_map             from the forward, or NULL (weights and texel coordinates are then recomputed; always so
+ *                       with NR_DETERMINISTIC)
  *   tile_list           from the forward, or NULL (then every tile is visited)
  *   grad_images         [B, C, S, S] upstream gradient
  *   grad_vertices       [B, nv, 3]   out, ACCUMULATED into (caller zero-fills)
@@ -239,7 +247,7 @@ NR_API int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices
 NR_API int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
                           const float *textures, const int32_t *face_index_map,
-                          const float *images_internal, const int32_t *tile_list,
+                          const float *images_internal, const float *aux_map, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
                           float *grad_vertices_textures, void *deterministic_scratch, const nrLights *lights,
                           void *stream);

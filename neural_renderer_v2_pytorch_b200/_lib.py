@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libnr_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NR_OK = 0
 NR_ERR_INVALID_ARGUMENT = 1
 NR_ERR_CUDA = 2
@@ -120,10 +120,10 @@ def lib():
     L.nr_workspace_bytes.argtypes = [ctypes.POINTER(RasterConfig), i64]
     L.nr_rasterize_forward.restype = ctypes.c_int
     L.nr_rasterize_forward.argtypes = [ctypes.POINTER(RasterConfig), vp, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       vp, vp, vp, ctypes.c_size_t, i64, vp, vp, ctypes.POINTER(ZeroFill),
+                                       vp, vp, vp, vp, ctypes.c_size_t, i64, vp, vp, ctypes.POINTER(ZeroFill),
                                        ctypes.POINTER(Lights), vp]
     L.nr_rasterize_backward.restype = ctypes.c_int
-    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 13 + [ctypes.POINTER(Lights), vp]
+    L.nr_rasterize_backward.argtypes = [ctypes.POINTER(RasterConfig)] + [vp] * 14 + [ctypes.POINTER(Lights), vp]
     L.nr_deterministic_scratch_bytes.restype = ctypes.c_size_t
     L.nr_deterministic_scratch_bytes.argtypes = [ctypes.POINTER(RasterConfig)]
     L.nr_differentiation_backward.restype = ctypes.c_int

@@ -212,8 +212,8 @@ size_t nr_workspace_bytes(const nrRasterConfig *cfg, int64_t pair_capacity) {
 int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                          const float *vertices_textures, const int32_t *faces_textures,
                          const float *textures, int32_t *face_index_map, float *weight_map,
-                         float *depth_map, float *images, float *images_internal, int32_t *tile_list,
-                         void *workspace, size_t workspace_bytes, int64_t pair_capacity,
+                         float *depth_map, float *images, float *images_internal, float *aux_map,
+                         int32_t *tile_list, void *workspace, size_t workspace_bytes, int64_t pair_capacity,
                          nrBinStats *stats_host, void *stats_event, const nrZeroFill *zero_fill,
                          const nrLights *lights, void *stream_) {
     if (int rc = check_config(cfg)) return rc;
@@ -296,6 +296,8 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     ra.dmap = depth_map;
     ra.images = images;
     ra.internal = images_internal;
+    if ((uintptr_t)aux_map & 7) return fail(NR_ERR_INVALID_ARGUMENT, "aux_map not 8-byte aligned");
+    ra.aux = aux_map;
     ra.faces = faces;
     ra.nv = cfg->num_vertices;
     ra.verts = vertices;
@@ -357,7 +359,7 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
 int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, const int32_t *faces,
                           const float *vertices_textures, const int32_t *faces_textures,
                           const float *textures, const int32_t *face_index_map,
-                          const float *images_internal, const int32_t *tile_list,
+                          const float *images_internal, const float *aux_map, const int32_t *tile_list,
                           const float *grad_images, float *grad_vertices, float *grad_textures,
                           float *grad_vertices_textures, void *deterministic_scratch, const nrLights *lights,
                           void *stream_) {
@@ -376,6 +378,7 @@ int nr_rasterize_backward(const nrRasterConfig *cfg, const float *vertices, cons
     a.tex = textures;
     a.fim = face_index_map;
     a.internal = images_internal;
+    a.aux = (cfg->flags & NR_DETERMINISTIC) ? nullptr : aux_map;
     a.grad_images = grad_images;
     a.tile_list = tile_list;
     a.sm_count = sm_count_cached();
@@ -525,7 +528,7 @@ int nr_face_index_map_forward_safe(const float *faces, int32_t *face_index, int3
     // the pinned statistics are owned by the call in flight until its event completes
     const bool track = !s.pending;
     int rc = nr_rasterize_forward(&cfg, faces, nullptr, nullptr, nullptr, nullptr, face_index, nullptr, nullptr, nullptr,
-                                  nullptr, nullptr, s.ptr, s.bytes, cap, track ? s.stats_host : nullptr,
+                                  nullptr, nullptr, nullptr, s.ptr, s.bytes, cap, track ? s.stats_host : nullptr,
                                   track ? (void *)s.stats_event : nullptr, nullptr, nullptr, stream);
     if (rc != NR_OK) return rc;
     if (track) {

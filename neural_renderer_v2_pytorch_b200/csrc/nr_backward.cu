@@ -89,13 +89,14 @@ __device__ __forceinline__ void clamp_shares(float x0, float lo, float hi, float
 template <bool NEED_UV>
 __device__ __forceinline__ void sample_texture_backward(const float *__restrict__ tex_b, int H, int W,
                                                         float eps, const float q[3], const float z[3],
-                                                        const float u[3], const float v[3],
+                                                        const float u[3], const float v[3], const float *aux,
                                                         const float g_lit[3], const float cw[3], float g[3],
                                                         float rgb_tex[3], int tap[4], float tw[4],
                                                         int &cell, float gz[3], float gu[3], float gv[3]) {
     // exact divisions like the forward: texel coordinates reach ~1e3, where the fast division's 2 ulp
-    // would move the bilinear weights by more than the 1e-5 gradient tolerance
-    const TexCoord tc = texel_coord<true>(q, z, u, v, eps);
+    // would move the bilinear weights by more than the 1e-5 gradient tolerance.  With the forward's aux map
+    // the three quotients are read back instead (aux = depth, nx, ny of this pixel).
+    const TexCoord tc = aux ? texel_coord_stored(aux[0], aux[1], aux[2], z, u, v, eps) : texel_coord<true>(q, z, u, v, eps);
     const float depth = tc.depth, nx = tc.nx, ny = tc.ny, x0 = tc.x0, y0 = tc.y0, xf = tc.xf, yf = tc.yf;
     const float *zz = tc.zz;
     const float ulo = fminf(u[0], fminf(u[1], u[2])), uhi = __fsub_rn(fmaxf(u[0], fmaxf(u[1], u[2])), eps);
@@ -196,7 +197,9 @@ __device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, Index
     }
 }
 
-template <int CT, bool NEED_UV, bool DET>
+// AUX: the forward left the normalised weights (and, with colour, the texel coordinate) of every foreground pixel
+// in the aux map: nothing of that is re-derived here (9 scattered vertex loads and 12 IEEE divisions less per pixel).
+template <int CT, bool NEED_UV, bool DET, bool AUX>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_backward(const BackwardArgs a) {
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
@@ -296,17 +299,33 @@ k_backward(const BackwardArgs a) {
             vid[0] = 3 * f; vid[1] = 3 * f + 1; vid[2] = 3 * f + 2;
         }
         const float *vb = a.verts + (size_t)b * a.nv * 3;
-        float X[3], Y[3], Z[3];
+        float Z[3] = {1.f, 1.f, 1.f}, q[3], tcs[3] = {0.f, 0.f, 0.f};
+        if (AUX) {
+            const float *ap = a.aux + (((size_t)b * R + yi) * R + xi) * (rgb ? 6 : 3);
+            if (rgb) {
+                const float2 a0 = __ldg(reinterpret_cast<const float2 *>(ap)), a1 = __ldg(reinterpret_cast<const float2 *>(ap) + 1),
+                             a2 = __ldg(reinterpret_cast<const float2 *>(ap) + 2);
+                q[0] = a0.x; q[1] = a0.y; q[2] = a1.x;
+                tcs[0] = a1.y; tcs[1] = a2.x; tcs[2] = a2.y;
+            } else {
+                q[0] = __ldg(ap); q[1] = __ldg(ap + 1); q[2] = __ldg(ap + 2);
+            }
+            if (has_z) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            X[k] = __ldg(vb + 3 * (size_t)vid[k]);
-            Y[k] = __ldg(vb + 3 * (size_t)vid[k] + 1);
-            Z[k] = __ldg(vb + 3 * (size_t)vid[k] + 2);
+                for (int k = 0; k < 3; ++k) Z[k] = __ldg(vb + 3 * (size_t)vid[k] + 2);
+            }
+        } else {
+            float X[3], Y[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                X[k] = __ldg(vb + 3 * (size_t)vid[k]);
+                Y[k] = __ldg(vb + 3 * (size_t)vid[k] + 1);
+                Z[k] = __ldg(vb + 3 * (size_t)vid[k] + 2);
+            }
+            const float xp = pix_center(xi, R), yp = pix_center(yi, R);
+            raw_weights(xp, yp, X[0], Y[0], X[1], Y[1], X[2], Y[2], q[0], q[1], q[2]);
+            normalize_weights<true>(q[0], q[1], q[2]);   // exact: 2 ulp on q move texel coordinates of ~1e3 by 1e-4
         }
-        const float xp = pix_center(xi, R), yp = pix_center(yi, R);
-        float q[3];
-        raw_weights(xp, yp, X[0], Y[0], X[1], Y[1], X[2], Y[2], q[0], q[1], q[2]);
-        normalize_weights<true>(q[0], q[1], q[2]);   // exact: 2 ulp on q move texel coordinates of ~1e3 by 1e-4
         float gz[3] = {0.f, 0.f, 0.f};
         int c0 = 0;
         if (rgb) {
@@ -340,8 +359,8 @@ k_backward(const BackwardArgs a) {
                             nrm[c] = __fadd_rn(nrm[c], __fmul_rn(q[k], __ldg(vnb + 3 * (size_t)vid[k] + c)));
                     light_weights(a.lights, b, a.B, nrm, cw, nullptr, nullptr);
                 }
-                sample_texture_backward<NEED_UV>(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, g_lit,
-                                        cw, g, rgb_tex, tap, tw, cell, gz, gu, gv);
+                sample_texture_backward<NEED_UV>(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, Z, u, v, AUX ? tcs : nullptr,
+                                        g_lit, cw, g, rgb_tex, tap, tw, cell, gz, gu, gv);
                 if (lit && a.lights.grad_vnormals) {
                     // d loss / d colour weight = upstream * unlit sample; then through the lights to the normal
                     const float gcw[3] = {g_lit[0] * rgb_tex[0], g_lit[1] * rgb_tex[1], g_lit[2] * rgb_tex[2]};
@@ -471,16 +490,24 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
     if (a.det_verts) {
-        if (a.grad_vt) k_backward<0, true, true><<<grid, block, 0, stream>>>(a);
-        else k_backward<0, false, true><<<grid, block, 0, stream>>>(a);
+        if (a.grad_vt) k_backward<0, true, true, false><<<grid, block, 0, stream>>>(a);
+        else k_backward<0, false, true, false><<<grid, block, 0, stream>>>(a);
     } else if (a.grad_vt) {
-        k_backward<0, true, false><<<grid, block, 0, stream>>>(a);
+        if (a.aux) k_backward<0, true, false, true><<<grid, block, 0, stream>>>(a);
+        else k_backward<0, true, false, false><<<grid, block, 0, stream>>>(a);
+    } else if (a.aux) {
+        switch (a.lights.num > 0 ? 0 : a.C) {
+            case 1: k_backward<1, false, false, true><<<grid, block, 0, stream>>>(a); break;
+            case 3: k_backward<3, false, false, true><<<grid, block, 0, stream>>>(a); break;
+            case 4: k_backward<4, false, false, true><<<grid, block, 0, stream>>>(a); break;
+            default: k_backward<0, false, false, true><<<grid, block, 0, stream>>>(a); break;
+        }
     } else {
         switch (a.lights.num > 0 ? 0 : a.C) {
-            case 1: k_backward<1, false, false><<<grid, block, 0, stream>>>(a); break;
-            case 3: k_backward<3, false, false><<<grid, block, 0, stream>>>(a); break;
-            case 4: k_backward<4, false, false><<<grid, block, 0, stream>>>(a); break;
-            default: k_backward<0, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 1: k_backward<1, false, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 3: k_backward<3, false, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 4: k_backward<4, false, false, false><<<grid, block, 0, stream>>>(a); break;
+            default: k_backward<0, false, false, false><<<grid, block, 0, stream>>>(a); break;
         }
     }
     cudaError_t e = cudaGetLastError();

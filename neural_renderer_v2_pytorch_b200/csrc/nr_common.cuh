@@ -272,6 +272,23 @@ __device__ __forceinline__ TexCoord texel_coord(const float q[3], const float z[
     return t;
 }
 
+// The same from the three quotients the forward stored (aux_map): no division left.
+__device__ __forceinline__ TexCoord texel_coord_stored(float depth, float nx, float ny, const float z[3], const float u[3],
+                                                       const float v[3], float eps) {
+    TexCoord t;
+    t.zz[0] = __fadd_rn(z[0], 1e-10f);
+    t.zz[1] = __fadd_rn(z[1], 1e-10f);
+    t.zz[2] = __fadd_rn(z[2], 1e-10f);
+    t.depth = depth;
+    t.nx = nx;
+    t.ny = ny;
+    t.x0 = __fmul_rn(nx, depth);
+    t.y0 = __fmul_rn(ny, depth);
+    t.xf = fminf(fmaxf(t.x0, fminf(u[0], fminf(u[1], u[2]))), __fsub_rn(fmaxf(u[0], fmaxf(u[1], u[2])), eps));
+    t.yf = fminf(fmaxf(t.y0, fminf(v[0], fminf(v[1], v[2]))), __fsub_rn(fmaxf(v[0], fmaxf(v[1], v[2])), eps));
+    return t;
+}
+
 // Lights as the kernels see them (include/nr_b200.h: nrLights).
 struct LightArgs {
     int num;

@@ -57,6 +57,7 @@ struct RasterArgs {
     float *dmap;            // [B, R, R] or null
     float *images;          // [B, C, S, S] or null (compat call renders no image)
     float *internal;        // [B, C, R, R] (AA) or null
+    float *aux;             // [B, R, R, 6 (rgb) or 3] forward -> backward state at foreground pixels, or null
     const int32_t *faces;   // [nf, 3] vertex ids (null: 3f..3f+2), only read when lights are on
     int nv;
     LightArgs lights;
@@ -89,6 +90,7 @@ struct BackwardArgs {
     const float *tex;
     const int32_t *fim;
     const float *internal;  // [B, C, R, R] flipped planar
+    const float *aux;       // the forward's aux map, or null (weights and texel coordinates are then recomputed)
     const float *grad_images;   // [B, C, S, S]
     const int32_t *tile_list;   // non-empty tiles of the forward, or null (all tiles)
     int sm_count;

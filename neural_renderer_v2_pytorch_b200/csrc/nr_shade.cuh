@@ -42,8 +42,8 @@ __device__ __forceinline__ float fast_zp(float w0, float w1, float w2, float iz0
 // q = weight map, z = face depths, uv = texel coordinates of the 3 face corners.
 __device__ __forceinline__ void sample_texture(const float *__restrict__ tex_b, int H, int W,
                                                float eps, const float q[3], const float z[3],
-                                               const float u[3], const float v[3], float rgb[3]) {
-    const TexCoord tc = texel_coord(q, z, u, v, eps);
+                                               const float u[3], const float v[3], float rgb[3], TexCoord &tc) {
+    tc = texel_coord(q, z, u, v, eps);
     const float xf = tc.xf, yf = tc.yf;
     const float xff = floorf(xf), yff = floorf(yf);
     const float xcf = __fadd_rn(xff, 1.f), ycf = __fadd_rn(yff, 1.f);
@@ -257,6 +257,11 @@ __device__ __forceinline__ void shade_block(const RasterArgs &a, int b, int xi, 
     const size_t pix = ((size_t)b * R + yi) * R + xi;
     float dm = 0.f;
     if (valid) a.fim[pix] = fg ? best : -1;
+    // forward -> backward state (nr_b200.h: aux_map): the weights here, the texel coordinate below
+    float *aux = (fg && a.aux) ? a.aux + pix * (RGB ? 6 : 3) : nullptr;
+    if (aux && !RGB) {
+        aux[0] = q[0]; aux[1] = q[1]; aux[2] = q[2];
+    }
     if (fg) {
         if (FULL && a.wmap) {
             float *w = a.wmap + pix * 3;
@@ -310,8 +315,15 @@ __device__ __forceinline__ void shade_block(const RasterArgs &a, int b, int xi, 
                     v[k] = uv.y;
                 }
                 const float z[3] = {bz0, bz1, bz2};
-                if (tex_ok) sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb);
+                TexCoord tc;
+                tc.depth = tc.nx = tc.ny = 0.f;
+                if (tex_ok) sample_texture(a.tex + (size_t)b * 3 * a.H * a.W, a.H, a.W, a.eps, q, z, u, v, rgb, tc);
                 else atomicOr(&a.hdr->bad_index, 2);
+                if (aux) {
+                    reinterpret_cast<float2 *>(aux)[0] = make_float2(q[0], q[1]);
+                    reinterpret_cast<float2 *>(aux)[1] = make_float2(q[2], tc.depth);
+                    reinterpret_cast<float2 *>(aux)[2] = make_float2(tc.nx, tc.ny);
+                }
                 if (FULL && a.lights.num > 0) {
                     // smooth normal map (rasterize.py:186-187) and light accumulation (:252-283)
                     float n[3] = {0.f, 0.f, 0.f}, cw[3];

@@ -42,6 +42,12 @@ FORCE_DENSE_RASTER = {"0": False, "1": True}.get(os.environ.get("NR_FORCE_DENSE_
 # the tiles of the batch, from an earlier call) is rasterized by the face-parallel kernel.
 DENSE_RASTER_ABOVE = 32
 
+# Forward -> backward state (nr_b200.h: aux_map): the forward stores the normalised weights and the texel
+# coordinate of every foreground pixel, the backward reads them instead of re-deriving them (9 scattered vertex
+# loads and 12 IEEE divisions per pixel).  Measured at config 2 (profiles/r2_aux_map_ab.txt): the backward gets
+# 4 us faster, the forward 5 us slower (100 MB more to write) - a wash, so it is off unless asked for.
+USE_AUX_MAP = os.environ.get("NR_USE_AUX_MAP", "0") == "1"
+
 # test hook: always bin with the general multi-kernel path (large meshes) instead of the one-kernel path
 FORCE_GENERAL_BINNING = False
 
@@ -209,9 +215,10 @@ def _zero_fill_struct(buffers):
     return ctypes.byref(z)
 
 
-def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None, zero=(), sparse=False):
+def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, backgrounds=None, zero=(), sparse=False,
+                  want_aux=False):
     """Enqueues nr_rasterize_forward on the current stream and returns without synchronising.
-    Returns (images, internal, fim, wmap, dmap, tile_list)."""
+    Returns (images, internal, fim, wmap, dmap, tile_list, aux)."""
     L = _lib.lib()
     dev = vertices.device
     B, S = cfg.batch, cfg.image_size
@@ -232,6 +239,10 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         internal = torch.empty((B, C, R, R), dtype=torch.float32, device=dev) if aa else None
         wmap = torch.empty((B, R, R, 3), dtype=torch.float32, device=dev) if want_maps else None
         dmap = torch.empty((B, R, R), dtype=torch.float32, device=dev) if want_maps else None
+        # forward -> backward state (weights and texel coordinates of the foreground pixels, see nr_b200.h)
+        aux = None
+        if want_aux and not (cfg.flags & _lib.NR_DETERMINISTIC):
+            aux = torch.empty((B, R, R, 6 if (cfg.flags & _lib.NR_DRAW_RGB) else 3), dtype=torch.float32, device=dev)
         # which binning this call takes: one kernel per view (small meshes), the general path, or the
         # general path over 8x8 tiles (dense meshes); the last two are learnt from earlier calls' statistics
         shape = (cfg.num_faces, R)
@@ -272,7 +283,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
             _capture_keepalive.append(ws)
         rc = L.nr_rasterize_forward(
             ctypes.byref(cfg), _ptr(vertices), _ptr(faces), _ptr(vt), _ptr(ft), _ptr(tex),
-            _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(tile_list),
+            _ptr(fim), _ptr(wmap), _ptr(dmap), _ptr(images), _ptr(internal), _ptr(aux), _ptr(tile_list),
             ctypes.c_void_p(aligned), ws.numel() - (aligned - base), capacity,
             ctypes.c_void_p(sc.stats.data_ptr()) if track else None, sc.event if track else None,
             _zero_fill_struct(zero), _lights_struct(lights, None, backgrounds), ctypes.c_void_p(stream))
@@ -280,7 +291,7 @@ def _forward_call(cfg, vertices, faces, vt, ft, tex, want_maps, lights=None, bac
         if track:
             sc.pending = True
         # with 8x8 tiles the list is of no use to the backward (it walks 16x16 tiles)
-        return images, internal, fim, wmap, dmap, (None if fine else tile_list)
+        return images, internal, fim, wmap, dmap, (None if fine else tile_list), aux
 
 
 def _validate_indices(idx, limit, what):
@@ -330,15 +341,19 @@ class _Rasterize(torch.autograd.Function):
             gtex = torch.empty_like(tex) if (need[2] and tex is not None) else None
             if gv is not None or gvt is not None or gtex is not None:
                 ctx.grad_bufs = (gv, gvt, gtex)
-        images, internal, fim, _, _, tile_list = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg,
-                                                               ctx.grad_bufs or (),
-                                                               sparse=not (bg is not None and need[4]))
+        images, internal, fim, _, _, tile_list, aux = _forward_call(cfg, v, faces, vt, faces_textures, tex, False, lights, bg,
+                                                                    ctx.grad_bufs or (),
+                                                                    sparse=not (bg is not None and need[4]),
+                                                                    want_aux=USE_AUX_MAP and ctx.grad_bufs is not None)
         ctx.cfg = cfg
         ctx.bg_dtype = backgrounds.dtype if backgrounds is not None else None
         ctx.has_tex = tex is not None
         ctx.has_lights = lights is not None
         ctx.in_dtypes = tuple(t.dtype if t is not None else None for t in (vertices, vertices_textures, textures, vertex_normals))
+        ctx.has_aux = aux is not None
         saved = [v, faces, fim, internal if internal is not None else images, tile_list]
+        if ctx.has_aux:
+            saved.append(aux)
         if ctx.has_tex:
             saved += [vt, faces_textures, tex]
         if ctx.has_lights:
@@ -354,6 +369,7 @@ class _Rasterize(torch.autograd.Function):
         lights = tuple(saved[-3:]) if ctx.has_lights else None
         if ctx.has_lights:
             saved = saved[:-3]
+        aux = saved.pop(5) if ctx.has_aux else None
         if ctx.has_tex:
             v, faces, fim, internal, tile_list, vt, ft, tex = saved
         else:
@@ -382,7 +398,7 @@ class _Rasterize(torch.autograd.Function):
             if cfg.flags & _lib.NR_DETERMINISTIC:
                 scratch = torch.zeros(L.nr_deterministic_scratch_bytes(ctypes.byref(cfg)) // 8, dtype=torch.int64, device=dev)
             rc = L.nr_rasterize_backward(ctypes.byref(cfg), _ptr(v), _ptr(faces), _ptr(vt), _ptr(ft),
-                                         _ptr(tex), _ptr(fim), _ptr(internal), _ptr(tile_list), _ptr(g), _ptr(gv),
+                                         _ptr(tex), _ptr(fim), _ptr(internal), _ptr(aux), _ptr(tile_list), _ptr(g), _ptr(gv),
                                          _ptr(gtex), _ptr(gvt), _ptr(scratch), _lights_struct(lights, gvn),
                                          ctypes.c_void_p(stream))
             _lib.check(rc, "nr_rasterize_backward")
@@ -459,7 +475,7 @@ def rasterize_maps(vertices, faces, params: RasterizeParam, hyperparams: Rasteri
     (``face_index_map`` :235, ``weight_map`` :236, depth :292) plus the images.  Test / debug aid."""
     cfg, faces_d, vt, ft, tex, vn, light_pack, bg = _prepare(vertices, faces, params, hyperparams)
     with torch.no_grad():
-        images, internal, fim, wmap, dmap, _ = _forward_call(
+        images, internal, fim, wmap, dmap, _, _ = _forward_call(
             cfg, _f32c(vertices), faces_d, _f32c(vt) if vt is not None else None, ft,
             _f32c(tex) if tex is not None else None, True,
             (light_pack[0], light_pack[1], _f32c(vn)) if light_pack is not None else None,

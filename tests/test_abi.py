@@ -40,7 +40,7 @@ def test_python_binding_lists_every_symbol(lib_path):
     L = _lib.lib()
     for s in _lib.SYMBOLS:
         assert hasattr(L, s)
-    assert L.nr_abi_version() == _lib.ABI_VERSION == 3
+    assert L.nr_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_no_torch_in_the_abi(lib_path):
@@ -65,10 +65,10 @@ def test_pure_host_entry_points(lib_path):
     big = L.nr_workspace_bytes(ctypes.byref(cfg), 1000000)
     assert big - small >= 4 * (1000000 - 1000) - 512 and small % 256 == 0
     # argument validation happens before any CUDA call
-    rc = L.nr_rasterize_forward(None, *([None] * 12), 0, 0, None, None, None, None, None)
+    rc = L.nr_rasterize_forward(None, *([None] * 13), 0, 0, None, None, None, None, None)
     assert rc == f.NR_ERR_INVALID_ARGUMENT and b"NULL" in L.nr_last_error()
     cfg.flags = 0
-    rc = L.nr_rasterize_forward(ctypes.byref(cfg), *([None] * 12), 0, 0, None, None, None, None, None)
+    rc = L.nr_rasterize_forward(ctypes.byref(cfg), *([None] * 13), 0, 0, None, None, None, None, None)
     assert rc == f.NR_ERR_INVALID_ARGUMENT and b"nothing to draw" in L.nr_last_error()
     assert L.nr_differentiation_backward(None, None, None, 1, 8, 3, None) == f.NR_ERR_INVALID_ARGUMENT
 

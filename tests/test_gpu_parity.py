@@ -583,7 +583,7 @@ def test_forward_zero_fills_the_gradient_accumulators(nr, S):
     cfg, faces_d, *_ = rz._prepare(vs, faces, nr.RasterizeParam(), hp)
     bufs = [torch.full((n,), float("nan"), device="cuda") for n in (1, 3, 4, 1021, 4096 * 3 + 2)]
     for group in (bufs[:4], bufs[4:]):
-        images, internal, fim, _, _, _ = rz._forward_call(cfg, vs.contiguous(), faces_d, None, None, None, False, zero=group)
+        images, internal, fim, _, _, _, _ = rz._forward_call(cfg, vs.contiguous(), faces_d, None, None, None, False, zero=group)
         for t in group:
             assert float(t.abs().sum()) == 0.0 and not torch.isnan(t).any()
         assert not torch.isnan(images).any() and not torch.isnan(internal).any()
@@ -812,6 +812,7 @@ def test_kernels_stay_inside_their_buffers(nr, S, aa, fine, general):
         return bool((big[:G_] == want).all()) and bool((big[G_ + n:] == want).all())
 
     sizes = dict(fim=(B * R * R, torch.int32), images=(B * 4 * S * S, torch.float32), internal=(B * 4 * R * R, torch.float32),
+                 aux=(B * R * R * 6, torch.float32),
                  tile_list=(8 + 16 * B * ntx * ntx, torch.int32), gv=(v.numel(), torch.float32), gtex=(tex.numel(), torch.float32),
                  gvt=(vt.numel(), torch.float32), ws=(int(L.nr_workspace_bytes(ctypes.byref(cfg), cap)) // 4 + 64, torch.int32))
     buf = {k: guarded(n, dt) for k, (n, dt) in sizes.items()}
@@ -824,17 +825,28 @@ def test_kernels_stay_inside_their_buffers(nr, S, aa, fine, general):
     base = (ws.data_ptr() + 255) & ~255
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     rc = L.nr_rasterize_forward(ctypes.byref(cfg), ptr(v), ptr(faces), ptr(vt), ptr(ft), ptr(tex), ptr(buf["fim"][1]), None, None,
-                                ptr(buf["images"][1]), ptr(buf["internal"][1]) if aa else None, ptr(buf["tile_list"][1]),
+                                ptr(buf["images"][1]), ptr(buf["internal"][1]) if aa else None, ptr(buf["aux"][1]),
+                                ptr(buf["tile_list"][1]),
                                 ctypes.c_void_p(base), ws.numel() * 4 - (base - ws.data_ptr()), cap, None, None,
                                 ctypes.byref(zf), None, stream)
     _lib.check(rc, "forward")
     G = torch.randn((B, 4, S, S), generator=g).cuda()
     saved = buf["internal"][1] if aa else buf["images"][1]
     rc = L.nr_rasterize_backward(ctypes.byref(cfg), ptr(v), ptr(faces), ptr(vt), ptr(ft), ptr(tex), ptr(buf["fim"][1]), ptr(saved),
-                                 None if fine else ptr(buf["tile_list"][1]), ptr(G), ptr(buf["gv"][1]), ptr(buf["gtex"][1]),
-                                 ptr(buf["gvt"][1]), None, None, stream)
+                                 ptr(buf["aux"][1]), None if fine else ptr(buf["tile_list"][1]), ptr(G), ptr(buf["gv"][1]),
+                                 ptr(buf["gtex"][1]), ptr(buf["gvt"][1]), None, None, stream)
     _lib.check(rc, "backward")
     torch.cuda.synchronize()
+    # the same backward WITHOUT the forward's aux map (weights and texel coordinates recomputed): same gradients
+    again = {k: torch.zeros_like(buf[k][1]) for k in ("gv", "gtex", "gvt")}
+    rc = L.nr_rasterize_backward(ctypes.byref(cfg), ptr(v), ptr(faces), ptr(vt), ptr(ft), ptr(tex), ptr(buf["fim"][1]), ptr(saved),
+                                 None, None if fine else ptr(buf["tile_list"][1]), ptr(G), ptr(again["gv"]),
+                                 ptr(again["gtex"]), ptr(again["gvt"]), None, None, stream)
+    _lib.check(rc, "backward without aux")
+    torch.cuda.synchronize()
+    for k, t in again.items():
+        scale = float(t.abs().max())
+        assert float((t - buf[k][1]).abs().max()) <= 2e-6 * scale, k
     for k, (n, _) in sizes.items():
         assert intact(buf[k][0], n), "%s: guard words overwritten" % k
     # and everything inside was written: no poison left in the outputs, gradients finite and non-trivial
