@@ -384,13 +384,11 @@ def run_ours(args):
         run_step()
     # ... and a dress rehearsal of the timed loop (untimed): on a fresh box the first few hundred replays can be
     # paced by the host (lazy initialisation in the driver), which is not what the metric is about
-    t_warm = time.perf_counter()
-    while True:
+    # (a fixed count: with a shared mesh every replay holds a collective, so the ranks must agree on it)
+    for _ in range(2):
         for _ in range(args.steps):
             run_step()
         torch.cuda.synchronize(dev)
-        if time.perf_counter() - t_warm > 0.3:
-            break
     barrier()
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
