@@ -332,7 +332,8 @@ def run_ours(args):
             # Renderer.render_silhouettes on the shared [1,nv,3] mesh with [B,3] viewpoints: the fused camera
             # transform projects it into every local view; its backward sums the gradient over the views in
             # registers, and share_across_ranks all-reduces the [1,nv,3] result over the ranks (parallel.py)
-            images = rend.render_silhouettes(nr.parallel.share_across_ranks(param), faces)
+            shared_param = param if args.no_collective else nr.parallel.share_across_ranks(param)
+            images = rend.render_silhouettes(shared_param, faces)
             ((images - target) ** 2).sum().backward()
             return images
     elif w.get("renderer"):
@@ -573,6 +574,11 @@ def run_ours(args):
                             "an optimisation loop whose loss is evaluated there"},
         "gpu_launches": int(round(launches_per_step * args.steps)),
         "launch_mode": "cuda graph replay of the whole step" if use_graph else "eager (python)",
+        "collective": (None if not shared or world == 1 else
+                       ("none (study: gradient left un-reduced)" if args.no_collective else
+                        ("fused into the camera backward kernel over NVLink peer memory"
+                         if nr.parallel.FUSED_ALLREDUCE and nr.parallel._Exchange.get(inp["nv"], None, dev) is not None
+                         else "ncclAllReduce"))),
         "host_ms_per_step": round(host_ms, 4),
         "clocks": clocks,
         "roofline": roofline,
@@ -699,6 +705,8 @@ def main():
                          "weak: every GPU renders the workload's batch (default for the others)")
     ap.add_argument("--views", type=int, default=0, help="override the workload's batch (single-GPU studies of the sharded sizes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-collective", action="store_true",
+                    help="cfg3 study only: leave the gradient of the shared mesh un-reduced (isolates the cost of the exchange)")
     ap.add_argument("--unfused-camera", action="store_true", help="cfg2r: camera transform as torch ops")
     ap.add_argument("--eager", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -282,6 +282,25 @@ NR_API int nr_camera_backward(const float *vertices, const float *rotation, cons
                               void *stream);
 
 /*
+ * Shared mesh on several GPUs of one box (BASELINE config 3: multi-view optimisation, 8 views per GPU): the
+ * shared-mesh camera backward FUSED with the all-reduce of its [1, nv, 3] result over NVLink peer memory - no
+ * NCCL call, no second kernel.  Every rank passes the same `peer_buffers`: world pointers, entry r = rank r's
+ * exchange buffer of nr_camera_exchange_bytes(nv, world) bytes as mapped into THIS process (symmetric memory /
+ * CUDA IPC; zero-filled once before the first call, then owned by these calls), and its own `epoch` (four ints of
+ * device memory, zero-filled once; epoch[2] becomes 1 if a peer failed to show up within a few seconds).  CTA j sums its 256 vertices over the local views, publishes the slice, waits
+ * for the same slice of every peer (flags in the exchange buffers, release / acquire at system scope), adds the
+ * world slices in rank order and writes grad_vertices: bit-identical on every rank and from run to run.  All ranks
+ * must call it the same number of times (it is a collective).  The grid must be resident as a whole
+ * (nv <= 256 * SMs * resident CTAs per SM: otherwise NR_ERR_INVALID_ARGUMENT, use NCCL).
+ */
+NR_API int nr_camera_exchange_bytes(int32_t num_vertices, int32_t world);
+NR_API int nr_camera_backward_shared_allreduce(const float *vertices, const float *rotation, const float *eye,
+                                               const float *grad_out, float *grad_vertices, float *partial,
+                                               int32_t batch, int32_t num_vertices, int32_t perspective, float width,
+                                               int32_t rank, int32_t world, void *const *peer_buffers,
+                                               int32_t *epoch, void *stream);
+
+/*
  * Same operator as face_index_map_forward_safe (rasterize_cuda.cpp:55-65):
  *   faces [B, nf, 3, 3], face_index [B*S*S] written in place (pre-fill not required).
  * `eps` is accepted and unused, like in the reference kernel.  Like the reference operator the call is

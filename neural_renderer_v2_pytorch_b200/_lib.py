@@ -34,7 +34,7 @@ SYMBOLS = (
     "nr_event_synchronize", "nr_event_query", "nr_deterministic_scratch_bytes", "nr_workspace_bytes", "nr_rasterize_forward", "nr_rasterize_backward",
     "nr_differentiation_backward", "nr_face_index_map_forward_safe", "nr_compute_weight_map",
     "nr_profile_enable", "nr_profile_collect", "nr_camera_partial_blocks", "nr_camera_forward",
-    "nr_camera_backward",
+    "nr_camera_backward", "nr_camera_exchange_bytes", "nr_camera_backward_shared_allreduce",
 )
 NR_PROF_SLOTS = 14
 PROF_SLOT_NAMES = ("memset", "setup_count", "scan_tiles", "scatter", "sort_long", "raster", "backward",
@@ -142,6 +142,11 @@ def lib():
     L.nr_camera_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
     L.nr_camera_backward.restype = ctypes.c_int
     L.nr_camera_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, vp]
+    L.nr_camera_exchange_bytes.restype = ctypes.c_int
+    L.nr_camera_exchange_bytes.argtypes = [i32, i32]
+    L.nr_camera_backward_shared_allreduce.restype = ctypes.c_int
+    L.nr_camera_backward_shared_allreduce.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32,
+                                                      ctypes.POINTER(vp), vp, vp]
     if L.nr_abi_version() != ABI_VERSION:
         raise RuntimeError("libnr_b200.so ABI version mismatch")
     _lib = L

@@ -24,7 +24,8 @@ class _CameraTransform(torch.autograd.Function):
     (deterministic, no [B,nv,3] intermediate and no separate reduction)."""
 
     @staticmethod
-    def forward(ctx, vertices, rotation, eye, perspective, width):
+    def forward(ctx, vertices, rotation, eye, perspective, width, exchange=None):
+        ctx.exchange = exchange
         v = vertices.detach().to(torch.float32).contiguous()
         r = rotation.detach().to(torch.float32).contiguous()
         e = eye.detach().to(torch.float32).contiguous()
@@ -53,20 +54,28 @@ class _CameraTransform(torch.autograd.Function):
         partial = None
         if need_cam:
             partial = torch.empty((B, L.nr_camera_partial_blocks(nv), 12), dtype=torch.float32, device=v.device)
+        ex = ctx.exchange
         with torch.cuda.device(v.device):
             stream = torch.cuda.current_stream(v.device).cuda_stream
-            rc = L.nr_camera_backward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
-                                      ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(g.data_ptr()),
-                                      ctypes.c_void_p(gv.data_ptr()),
-                                      ctypes.c_void_p(partial.data_ptr()) if partial is not None else None, B, nv,
-                                      ctx.perspective, ctx.width, ctx.shared, ctypes.c_void_p(stream))
+            pp = ctypes.c_void_p(partial.data_ptr()) if partial is not None else None
+            if ex is not None:
+                # shared mesh on several GPUs: the sum over the local views AND over the ranks, in this one kernel
+                rc = L.nr_camera_backward_shared_allreduce(
+                    ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()), ctypes.c_void_p(e.data_ptr()),
+                    ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(gv.data_ptr()), pp, B, nv, ctx.perspective, ctx.width,
+                    ex.rank, ex.world, ex.pointers, ctypes.c_void_p(ex.epoch.data_ptr()), ctypes.c_void_p(stream))
+            else:
+                rc = L.nr_camera_backward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(r.data_ptr()),
+                                          ctypes.c_void_p(e.data_ptr()), ctypes.c_void_p(g.data_ptr()),
+                                          ctypes.c_void_p(gv.data_ptr()), pp, B, nv,
+                                          ctx.perspective, ctx.width, ctx.shared, ctypes.c_void_p(stream))
         _lib.check(rc, "nr_camera_backward")
         if gv.dtype != ctx.in_dtype:
             gv = gv.to(ctx.in_dtype)
         if not need_cam:
-            return gv, None, None, None, None
+            return gv, None, None, None, None, None
         red = partial.sum(1)                               # fixed-order reduction of the per-block sums
-        return gv, red[:, :9].reshape(B, 3, 3), red[:, 9:], None, None
+        return gv, red[:, :9].reshape(B, 3, 3), red[:, 9:], None, None, None
 
 
 def transform_vertices(vertices, viewpoints, camera_mode="look_at", camera_direction=None, perspective=True,
@@ -98,4 +107,12 @@ def transform_vertices(vertices, viewpoints, camera_mode="look_at", camera_direc
     if torch.is_tensor(viewing_angle):
         raise TypeError("the fused transform takes a scalar viewing angle; use look_at + perspective for a tensor")
     width = float(torch.tan(torch.tensor(float(viewing_angle), dtype=torch.float32) / 180. * _PI_REF))
-    return _CameraTransform.apply(vertices, rot, eye.expand(B, 3), bool(perspective), width)
+    exchange = None
+    shared = getattr(vertices, "_nr_shared", None)
+    if shared is not None and vertices.shape[0] == 1 and B > 1 and vertices.shape[1] <= 256 * 128 * 4:      # (its grid must be resident)
+        # a mesh shared by every rank (parallel.share_across_ranks): exchange its gradient inside the camera backward
+        from . import parallel
+        exchange = parallel._Exchange.get(vertices.shape[1], shared[1], vertices.device)
+        if exchange is not None:
+            vertices = shared[0]
+    return _CameraTransform.apply(vertices, rot, eye.expand(B, 3), bool(perspective), width, exchange)

@@ -61,6 +61,50 @@ def share_across_views(param, local_views, group=None):
     return _ShareAcrossViews.apply(param, local_views, group)
 
 
+class _Exchange:
+    """Symmetric-memory exchange buffers for the fused camera-backward + all-reduce kernel
+    (csrc/nr_camera.cu: k_camera_backward_shared_exchange): every rank maps every rank's buffer over NVLink."""
+
+    _cache = {}
+
+    def __init__(self, nv, group, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        L = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = L.nr_camera_exchange_bytes(nv, self.world)
+        if nbytes <= 0:
+            raise RuntimeError("mesh too large for the exchange buffer")
+        self.nv = nv
+        self.buffer = symm.empty((nbytes + 3) // 4, dtype=torch.int32, device=device)
+        self.buffer.zero_()
+        self.handle = symm.rendezvous(self.buffer, group if group is not None else dist.group.WORLD)
+        self.pointers = (ctypes.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.epoch = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                 # every rank's buffer is zeroed before anybody's first exchange
+
+    @classmethod
+    def get(cls, nv, group, device):
+        """The exchange of (group, mesh size, device), or None when peer memory cannot be set up (then NCCL)."""
+        key = (id(group) if group is not None else 0, nv, str(device))
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(nv, group, device)
+            except Exception as e:          # no symmetric memory on this system / backend: the NCCL path stays
+                import warnings
+                warnings.warn("fused all-reduce over peer memory unavailable (%s: %s); using %s all_reduce"
+                              % (type(e).__name__, e, dist.get_backend(group)))
+                cls._cache[key] = None
+        return cls._cache[key]
+
+
+# The fused exchange is a collective every rank must enter the same number of times; set to False (or
+# NR_FUSED_ALLREDUCE=0) to keep the NCCL all-reduce.
+FUSED_ALLREDUCE = __import__("os").environ.get("NR_FUSED_ALLREDUCE", "1") == "1"
+
+
 class _ShareAcrossRanks(torch.autograd.Function):
     """Identity; the backward sums the gradient over the ranks (in place, on the stream of the backward, so a
     captured step replays the collective too)."""
@@ -82,8 +126,19 @@ def share_across_ranks(param, group=None):
     """Mark ``param`` (e.g. ONE mesh [1,nv,3] handed to ``Renderer.render*`` with per-view ``viewpoints`` [B,3]:
     the fused camera transform projects it into the local views and sums its gradient over them) as shared by
     every rank: after ``backward()`` ``param.grad`` is the sum over ALL views of the job, identical on every
-    rank.  The all-reduce moves 12*nv bytes (vertices) or 12*T (textures) per step."""
-    return _ShareAcrossRanks.apply(param, group)
+    rank.  The all-reduce moves 12*nv bytes (vertices) or 12*T (textures) per step.
+
+    A [1,nv,3] CUDA mesh that goes into the fused camera transform (``Renderer.transform_vertices``) does not
+    even see a separate all-reduce: its camera-backward kernel exchanges the gradient slices with the peer GPUs
+    over NVLink itself (``_Exchange``), in rank order, so the result is bit-identical on every rank."""
+    out = _ShareAcrossRanks.apply(param, group)
+    if (FUSED_ALLREDUCE and param.is_cuda and param.ndim == 3 and param.shape[0] == 1 and param.shape[2] == 3
+            and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+            and dist.get_backend(group) == "nccl"):
+        # camera.transform_vertices takes `param` itself as its autograd input when it fuses the exchange, so
+        # this node only reduces what OTHER consumers of `out` send back
+        out._nr_shared = (param, group)
+    return out
 
 
 def allreduce_shared_grads(params, group=None):

@@ -56,8 +56,54 @@ def main():
     same = all(torch.equal(gathered[0], t) for t in gathered)
     if rank == 0:
         print("all ranks hold identical gradients:", same)
-    dist.destroy_process_group()
-    sys.exit(0 if (ok and same) else 1)
+
+    # ---- the same through Renderer on the [1,nv,3] mesh itself: the camera backward exchanges the gradient slices
+    # with the peers over NVLink inside the kernel (parallel._Exchange), no NCCL call in the step
+    rend = nr.Renderer()
+    rend.image_size, rend.anti_aliasing, rend.viewpoints, rend.deterministic = S, False, eye[lo:hi], True
+
+    def fused_step(p):
+        img = rend.render_silhouettes(nr.parallel.share_across_ranks(p), faces)
+        (img * G[lo:hi]).sum().backward()
+
+    # reference for it: the same Renderer step with the exchange switched off (NCCL all-reduce of the [1,nv,3] sum)
+    nr.parallel.FUSED_ALLREDUCE = False
+    p1 = torch.from_numpy(d["vertices"])[None].to(dev).requires_grad_(True)
+    fused_step(p1)
+    nr.parallel.FUSED_ALLREDUCE = True
+    p2 = torch.from_numpy(d["vertices"])[None].to(dev).requires_grad_(True)
+    fused_step(p2)
+    ex = nr.parallel._Exchange.get(p2.shape[1], None, dev)
+    used = ex is not None
+    scale = p1.grad.abs().max().item()
+    err2 = (p2.grad - p1.grad).abs().max().item() / scale         # summation order over the ranks is the only difference
+    # many steps in a row (epochs, buffer parity), eagerly and replayed from a CUDA graph; every step must give the
+    # same bits (deterministic rasterizer backward + rank-ordered exchange)
+    first = p2.grad.clone()
+    stable = True
+    for _ in range(40):
+        p2.grad = None
+        fused_step(p2)
+        stable &= torch.equal(p2.grad, first)
+    replay = nr.capture_step(lambda: fused_step(p2), params=[p2], warmup=2)
+    for _ in range(40):
+        replay()
+        stable &= torch.equal(p2.grad, first)
+    torch.cuda.synchronize()
+    timed_out = int(ex.epoch[2]) if used else 0
+    g2 = [torch.empty_like(first) for _ in range(world)]
+    dist.all_gather(g2, p2.grad)
+    same2 = all(torch.equal(g2[0], t) for t in g2)
+    ok2 = err2 < 2e-6 and stable and same2 and not timed_out
+    if rank == 0:
+        print("fused exchange in use: %s; vs NCCL path: max rel-to-scale error %.3g; 80 steps bit-stable: %s; identical on "
+              "all ranks: %s; peer time-outs: %d -> %s" % (used, err2, stable, same2, timed_out, "OK" if ok2 else "MISMATCH"))
+    ok = ok and ok2
+    flag = torch.tensor([1 if (ok and same) else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0 if int(flag.item()) else 1)      # (no NCCL teardown: a captured graph holds the communicator)
 
 
 if __name__ == "__main__":
