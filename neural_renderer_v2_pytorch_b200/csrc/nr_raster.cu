@@ -72,6 +72,13 @@ constexpr int RASTER_WARPS = TILE_THREADS / 32;
 #ifndef NR_LAZY_Z
 #define NR_LAZY_Z 1
 #endif
+// NR_CPASYNC_STAGE (experiment, profiles/r2_cpasync_ab.txt): the 48-byte record of the NEXT group's face goes
+// global -> shared with three cp.async (LDGSTS) per lane into a per-warp double buffer instead of three LDG.128
+// into registers.  The records a warp needs are a gather (tile list -> record), so a bulk-tensor TMA copy has
+// nothing contiguous to move; cp.async is the asynchronous copy that fits, and it was measured.
+#ifndef NR_CPASYNC_STAGE
+#define NR_CPASYNC_STAGE 0
+#endif
 constexpr int REC_Q = NR_LAZY_Z ? 5 : 4;       // float4 per staged face
 
 __device__ __noinline__ float exact_zp_call(float w0, float w1, float w2, float z0, float z1, float z2) {
@@ -88,6 +95,9 @@ k_raster(const RasterArgs a) {
     // a tile is 16x16 pixels = 8 warp blocks (8x4 each), or in the FINE variants 8x8 = 2 blocks
     constexpr int TSZ = FINE ? FINE_TILE : TILE, BLK_SHIFT = FINE ? 1 : 3, BLKS = 1 << BLK_SHIFT;
     __shared__ float4 s_rec[RASTER_WARPS][32][REC_Q];
+#if NR_CPASYNC_STAGE
+    __shared__ float4 s_stage[RASTER_WARPS][2][32][3];
+#endif
     __shared__ uint32_t s_bb[RASTER_WARPS][32];
 
     // If the pair list did not fit the workspace, the lists are unusable: every block then scans ALL
@@ -172,20 +182,46 @@ k_raster(const RasterArgs a) {
         auto load_id = [&](int i) -> int { return i < n ? (overflow ? i : __ldg(list + i)) : -1; };
         int fid_next = load_id(lane);
         int fid_next2 = load_id(32 + lane);
+#if NR_CPASYNC_STAGE
+        int stage = 0;
+        auto stage_record = [&](int st, int f_) {
+            if (f_ >= 0) {
+                const float4 *rp = reinterpret_cast<const float4 *>(rec_b + f_);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_stage[wid][st][lane][0]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(rp + 1));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(rp + 2));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage_record(0, fid_next);
+#else
         float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0;
         if (fid_next >= 0) {
             const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid_next);
             n0 = __ldg(rp); n1 = __ldg(rp + 1); n2 = __ldg(rp + 2);
         }
+#endif
         for (int g = 0; g < n; g += 32) {
             // ---- one face per lane: cull against this warp's block, compact the survivors
             const int fid = fid_next;
+#if NR_CPASYNC_STAGE
+            fid_next = fid_next2;
+            stage_record(stage ^ 1, fid_next);                    // next group's records in flight ...
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // ... while this group's have landed
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+            if (fid >= 0) {
+                q0 = s_stage[wid][stage][lane][0]; q1 = s_stage[wid][stage][lane][1]; q2 = s_stage[wid][stage][lane][2];
+            }
+            stage ^= 1;
+#else
             const float4 q0 = n0, q1 = n1, q2 = n2;
             fid_next = fid_next2;
             if (fid_next >= 0) {
                 const float4 *rp = reinterpret_cast<const float4 *>(rec_b + fid_next);
                 n0 = __ldg(rp); n1 = __ldg(rp + 1); n2 = __ldg(rp + 2);
             }
+#endif
             fid_next2 = load_id(g + 64 + lane);
             bool hit = false;
             if (fid >= 0) {
