@@ -579,12 +579,14 @@ def run_ours(args):
     bin_stats = None
     try:
         from neural_renderer_v2_pytorch_b200 import rasterize as _rz
-        for (di, _), sc in _rz._Scratch._cache.items():
+        bin_stats = []
+        for (di, st_), sc in _rz._Scratch._cache.items():
             if di == dev.index and sc.last_shape is not None:
                 sc.poll(block=True)
                 t_, m_, o_, b_ = sc.stats.tolist()
-                bin_stats = {"total_pairs": t_, "max_tile_faces": m_, "overflow": o_, "bad_index": b_,
-                             "path": "zbuf" if sc.last_dense else ("one-kernel binning" if sc.last_small else "general binning")}
+                bin_stats.append({"stream": "%x" % st_, "total_pairs": t_, "max_tile_faces": m_, "overflow": o_, "bad_index": b_,
+                                  "path": "zbuf" if sc.last_dense else ("one-kernel binning" if sc.last_small else "general binning"),
+                                  "dense_shapes": len(sc.dense), "fine_shapes": len(sc.fine_tiles)})
     except Exception:
         pass
 

@@ -130,25 +130,26 @@ __device__ __forceinline__ bool zb_setup(const RasterArgs &a, int b, int f, ZbFa
 
 // ---------------------------------------------------------------------------------------------- pass 1
 // A CTA owns 256 consecutive (view, face) pairs.  Their pixel boxes differ wildly (1 .. hundreds of pixels), so
-// "one thread walks its own face" leaves most lanes idle; instead the boxes of the CTA are laid end to end
-// (prefix sum of their areas in shared memory) and every thread tests the SAME number of consecutive
-// (face, pixel) items, ZB_ROUND per round.  The items that pass the inside test are compacted into a
-// shared-memory queue (one ballot + one shared atomic per warp and item), and the queue is then drained four
-// entries per thread at a time: four cheap depths, four atomicMin issued back to back, then the four checks.
-// The atomicMin has to RETURN the old minimum, a round trip to L2 of about a microsecond under load: the
-// kernel lives on how many of them it keeps in flight.
-constexpr int ZB_ROUND = 16;        // items per thread and round
-constexpr int ZB_HUGE = 4096;       // larger pixel boxes (r, c no longer fit 12 bits) are walked by a whole warp, unqueued
+// "one thread walks its own face" leaves most lanes idle; instead the ROWS of all the boxes of the CTA are laid end
+// to end (prefix sum of the box heights in shared memory) and every thread tests the same number of consecutive
+// (face, row) items, a row per round: the columns of the row in a tight loop, coverage as a bit mask.  The
+// pixels that pass the inside test are compacted into the warp's queue in shared memory (one warp scan per
+// round), and the queue is drained four entries per lane at a time: four cheap depths, four atomicMin issued
+// back to back, then the four checks.  The atomicMin has to RETURN the old minimum, a round trip to L2 of about
+// a microsecond under load: the kernel lives on how many of them it keeps in flight.
+constexpr int ZB_QUEUE = 1536;      // queue entries per warp; a round adds at most 32 lanes x 32 columns
+constexpr int ZB_FLUSH = ZB_QUEUE - 1024;
+constexpr int ZB_HUGE = 4096;       // pixel boxes larger than this, or wider than 32 columns, are walked by a whole warp, unqueued
 
 struct ZbFacesShared {
-    // of the CTA's faces: v = x0 y0 x1 y1 x2 y2 | dx10 dy10 dx21 dy21 dx02 dy02 | k0 k1 k2 | iz0 iz1 iz2 (ZbFace);
+    // of the CTA's faces: v = x0 y0 x1 y1 x2 y2 | dx10 dy10 dx21 dy21 dx02 dy02 | k0 k1 k2 | iz0 iz1 iz2 (ZbFace)
     float v[18][ZB_THREADS];
     int box[ZB_THREADS];            // xlo | ylo << 16
     int wh[ZB_THREADS];             // width | height << 16 of the pixel box
     int irregular[ZB_THREADS];      // depths that are not ordinary positive numbers (face_z_regular)
     int fid[ZB_THREADS], view[ZB_THREADS];
-    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the areas (dead and huge faces count 0)
-    unsigned hits[ZB_THREADS / 32][32 * ZB_ROUND];      // per warp: face (local) << 24 | row << 12 | column, inside the box
+    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the box heights (dead and huge faces count 0)
+    unsigned hits[ZB_THREADS / 32][ZB_QUEUE];           // per warp: face (local) << 24 | row << 12 | column, inside the box
     int wsum[ZB_THREADS / 32];
 };
 
@@ -170,7 +171,8 @@ __device__ __forceinline__ void zb_whole_face_from_shared(const ZbFacesShared &s
 template <bool POW2>
 __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_faces(const RasterArgs a) {
-    __shared__ ZbFacesShared sh;
+    extern __shared__ __align__(16) unsigned char zb_dynamic_smem[];
+    ZbFacesShared &sh = *reinterpret_cast<ZbFacesShared *>(zb_dynamic_smem);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int R = a.R;
     const PixGrid grid(R);
@@ -179,7 +181,7 @@ k_zb_faces(const RasterArgs a) {
     const bool in = idx < (long long)a.B * a.nf;
     const int b = in ? (int)(idx / a.nf) : 0, f = in ? (int)(idx % a.nf) : 0;
     // ---- per-face setup (rasterize.py:232, :94-104, :118-121)
-    int area = 0;
+    int area = 0, rows_mine = 0;
     bool huge = false;
     {
         FaceRec r;
@@ -188,7 +190,8 @@ k_zb_faces(const RasterArgs a) {
                                                   r, xlo, xhi, ylo, yhi, a.hdr);
         const int w = xhi - xlo + 1, h = yhi - ylo + 1;
         if (alive) area = w * h;
-        huge = area > ZB_HUGE;
+        huge = area > ZB_HUGE || (alive && w > 32);
+        rows_mine = (alive && !huge) ? h : 0;
         // the exact pixel box for the collect pass, which then needs no vertices for faces that touch nothing contested
         if (in) a.zb_box[idx] = alive ? make_uint2((unsigned)xlo | ((unsigned)xhi << 16), (unsigned)ylo | ((unsigned)yhi << 16))
                                       : make_uint2(DEAD_BBOX, 0u);
@@ -206,7 +209,7 @@ k_zb_faces(const RasterArgs a) {
     }
     // ---- the boxes end to end
     {
-        const int my = huge ? 0 : area;
+        const int my = rows_mine;
         int inc = my;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -227,8 +230,8 @@ k_zb_faces(const RasterArgs a) {
     const int chunk = (W + ZB_THREADS - 1) / ZB_THREADS;
     int pos = min(tid * chunk, W);
     const int end = min(pos + chunk, W);
-    // ---- my first item: face i = the one with pre[i] <= pos < pre[i + 1], then row and column inside its box
-    int i = 0, r = 0, c = 0, nxt = 0, fw = 1, fx = 0, fy = 0;
+    // ---- my first item: face i = the one with pre[i] <= pos < pre[i + 1], then the row inside its box
+    int i = 0, r = 0, nxt = 0, fw = 1, fx = 0, fy = 0;
     float x0 = 0.f, y0 = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, dx10 = 0.f, dy10 = 0.f, dx21 = 0.f, dy21 = 0.f, dx02 = 0.f, dy02 = 0.f;
     auto load_face = [&](int j) {
         x0 = sh.v[0][j]; y0 = sh.v[1][j]; x1 = sh.v[2][j]; y1 = sh.v[3][j]; x2 = sh.v[4][j]; y2 = sh.v[5][j];
@@ -246,44 +249,49 @@ k_zb_faces(const RasterArgs a) {
         }
         i = lo - 1;
         load_face(i);
-        const int k = pos - sh.pre[i];
-        r = k / fw;
-        c = k - r * fw;
+        r = pos - sh.pre[i];
     }
-    const unsigned lt_mask = (1u << lane) - 1u;
-    // The warps run on their own from here: the items of a warp's 32 threads go through the warp's own queue.
+    // The warps run on their own from here: the rows of a warp's 32 threads go through the warp's own queue.
     unsigned *queue = sh.hits[wid];
-    const int rounds = (wid * 32 * chunk < W) ? (chunk + ZB_ROUND - 1) / ZB_ROUND : 0;
+    const int rounds = (wid * 32 * chunk < W) ? chunk : 0;
+    int H = 0;                                                  // queue fill, warp-uniform
     for (int round = 0; round < rounds; ++round) {
-        // (a round: ZB_ROUND items of every thread of the warp)
-        // ---- phase A: inside tests (:107-116), hits into the queue
-        int H = 0;                                             // warp-uniform
-#pragma unroll 1
-        for (int j = 0; j < ZB_ROUND; ++j) {
-            bool hit = false;
-            unsigned code = 0u;
-            if (pos < end) {
-                const float xp = center(fx + c), yp = center(fy + r);
-                const float c1 = __fmaf_rn(__fsub_rn(yp, y0), dx10, -__fmul_rn(dy10, __fsub_rn(xp, x0)));
-                const float c2 = __fmaf_rn(__fsub_rn(yp, y1), dx21, -__fmul_rn(dy21, __fsub_rn(xp, x1)));
-                const float c3 = __fmaf_rn(__fsub_rn(yp, y2), dx02, -__fmul_rn(dy02, __fsub_rn(xp, x2)));
-                hit = !((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f));
-                code = ((unsigned)i << 24) | ((unsigned)r << 12) | (unsigned)c;
-                ++pos;
-                if (++c == fw) {
-                    c = 0;
-                    ++r;
-                }
-                if (pos == nxt && pos < end) {
-                    do ++i; while (sh.pre[i + 1] == sh.pre[i]);       // (faces without items)
-                    load_face(i);
-                    r = 0;
-                }
+        // ---- phase A: one row per lane, inside tests (:107-116) over its columns, hits into the queue
+        unsigned mask = 0u, code = 0u;
+        if (pos < end) {
+            const float yp = center(fy + r);
+            const float a1 = __fsub_rn(yp, y0), a2 = __fsub_rn(yp, y1), a3 = __fsub_rn(yp, y2);
+            for (int c = 0; c < fw; ++c) {
+                const float xp = center(fx + c);
+                const float c1 = __fmaf_rn(a1, dx10, -__fmul_rn(dy10, __fsub_rn(xp, x0)));
+                const float c2 = __fmaf_rn(a2, dx21, -__fmul_rn(dy21, __fsub_rn(xp, x1)));
+                const float c3 = __fmaf_rn(a3, dx02, -__fmul_rn(dy02, __fsub_rn(xp, x2)));
+                if (!((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f))) mask |= 1u << c;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (hit) queue[H + __popc(m & lt_mask)] = code;
-            H += __popc(m);
+            code = ((unsigned)i << 24) | ((unsigned)r << 12);
+            ++pos;
+            ++r;
+            if (pos == nxt && pos < end) {
+                do ++i; while (sh.pre[i + 1] == sh.pre[i]);       // (faces without rows)
+                load_face(i);
+                r = 0;
+            }
         }
+        // exclusive scan of the hit counts over the lanes: where this lane's hits go
+        const int cnt = __popc(mask);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        int slot = H + inc - cnt;
+        while (mask) {
+            queue[slot++] = code | (unsigned)(__ffs(mask) - 1);
+            mask &= mask - 1;
+        }
+        H += __shfl_sync(0xffffffffu, inc, 31);
+        if (H <= ZB_FLUSH && round + 1 < rounds) continue;
         __syncwarp();
         // ---- phase B: the queue, four entries per lane at a time
         for (int hb = 0; hb < H; hb += 4 * 32) {
@@ -296,11 +304,11 @@ k_zb_faces(const RasterArgs a) {
                 const int h = hb + k * 32 + lane;
                 go[k] = false;
                 if (h < H) {
-                    const unsigned code = queue[h];
-                    const int li = code >> 24;
+                    const unsigned hc = queue[h];
+                    const int li = hc >> 24;
                     ZbFace F;
                     zb_face_from_shared(sh, li, F);
-                    const int x = (sh.box[li] & 0xffff) + (int)(code & 0xfff), y = (int)((unsigned)sh.box[li] >> 16) + (int)((code >> 12) & 0xfff);
+                    const int x = (sh.box[li] & 0xffff) + (int)(hc & 0xfff), y = (int)((unsigned)sh.box[li] >> 16) + (int)((hc >> 12) & 0xfff);
                     bv[k] = sh.view[li];
                     fv[k] = F.fid;
                     pxy[k] = x | (y << 16);
@@ -314,6 +322,7 @@ k_zb_faces(const RasterArgs a) {
             for (int k = 0; k < 4; ++k)
                 if (go[k]) zb_check(a, zf[k], old[k], bv[k], pxy[k] & 0xffff, pxy[k] >> 16);
         }
+        H = 0;
         __syncwarp();
     }
     // ---- huge faces: the whole warp walks the box of one of its lanes' faces, a lane per pixel: the lanes form
@@ -448,7 +457,7 @@ k_zb_collect(const RasterArgs a) {
     };
     if (tid == 0) s_n = 0;
     __syncthreads();
-    const bool huge = alive && (xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE;
+    const bool huge = alive && ((xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE || xhi - xlo + 1 > 32);
     if (alive && !huge) {
         // coarse test: most faces touch no contested pixel; the few that do are queued, so that the costly part
         // (vertices, exact depths) runs on full warps
@@ -704,8 +713,16 @@ cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
     const unsigned face_ctas = (unsigned)((faces + ZB_THREADS - 1) / ZB_THREADS);
     if (face_ctas) {
         ProfScope p(PROF_ZB_FACES, stream);
-        if ((a.R & (a.R - 1)) == 0) k_zb_faces<true><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
-        else k_zb_faces<false><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            if ((e = cudaFuncSetAttribute(k_zb_faces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbFacesShared))) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(k_zb_faces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbFacesShared))) != cudaSuccess) return e;
+            attr_set[dev] = true;
+        }
+        if ((a.R & (a.R - 1)) == 0) k_zb_faces<true><<<face_ctas, ZB_THREADS, sizeof(ZbFacesShared), stream>>>(a);
+        else k_zb_faces<false><<<face_ctas, ZB_THREADS, sizeof(ZbFacesShared), stream>>>(a);
     }
     {
         ProfScope p(PROF_ZB_RESOLVE, stream);
