@@ -433,23 +433,17 @@ __device__ __forceinline__ void zb_collect_pixel(const RasterArgs &a, const ZbFa
     a.zb_nodes[node] = make_int4(F.fid, __float_as_int(zp), __float_as_int(zc), next);
 }
 
+constexpr int ZB_COLLECT_PER_THREAD = 4;        // faces per thread: four box loads (and the coarse lookups behind them) in flight
+
 __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_collect(const RasterArgs a) {
-    __shared__ int s_queue[ZB_THREADS];
+    __shared__ int s_queue[ZB_THREADS * ZB_COLLECT_PER_THREAD];
     __shared__ int s_n;
     if (a.hdr->zb_slots == 0) return;                     // nothing contested (uniform over the grid)
     const int tid = threadIdx.x, lane = tid & 31;
-    const long long cta0 = (long long)blockIdx.x * ZB_THREADS, idx = cta0 + tid;
+    const long long total = (long long)a.B * a.nf;
+    const long long cta0 = (long long)blockIdx.x * (ZB_THREADS * ZB_COLLECT_PER_THREAD);
     const PixGrid grid(a.R);
-    const bool in = idx < (long long)a.B * a.nf;
-    const int b = in ? (int)(idx / a.nf) : 0;
-    // the face's pixel box as pass 1 found it
-    int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
-    if (in) {
-        const uint2 box = __ldg(a.zb_box + idx);
-        xlo = (int)(box.x & 0xffff); xhi = (int)(box.x >> 16); ylo = (int)(box.y & 0xffff); yhi = (int)(box.y >> 16);
-    }
-    const bool alive = in && xlo <= xhi;
     // bits of columns [c0, c1] in bitmap word wq
     auto col_mask = [](int wq, int c0, int c1) -> unsigned {
         const int lo = max(c0 - wq * 32, 0), hi = min(c1 - wq * 32, 31);
@@ -457,19 +451,35 @@ k_zb_collect(const RasterArgs a) {
     };
     if (tid == 0) s_n = 0;
     __syncthreads();
-    const bool huge = alive && ((xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE || xhi - xlo + 1 > 32);
-    if (alive && !huge) {
-        // coarse test: most faces touch no contested pixel; the few that do are queued, so that the costly part
-        // (vertices, exact depths) runs on full warps
-        bool any = false;
-        for (int cy = ylo >> 3; cy <= (yhi >> 3); ++cy)
-            for (int wq = xlo >> 5; wq <= (xhi >> 5); ++wq)
-                any |= (__ldg(a.zb_coarse + ((size_t)b * a.zb_crows + cy) * a.zb_wpr + wq) & col_mask(wq, xlo, xhi)) != 0u;
-        if (any) s_queue[atomicAdd(&s_n, 1)] = tid;
+    // the faces' pixel boxes as pass 1 found them
+    uint2 box[ZB_COLLECT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < ZB_COLLECT_PER_THREAD; ++k) {
+        const long long idx = cta0 + k * ZB_THREADS + tid;
+        box[k] = idx < total ? __ldg(a.zb_box + idx) : make_uint2(DEAD_BBOX, 0u);
+    }
+    unsigned huge_mask[ZB_COLLECT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < ZB_COLLECT_PER_THREAD; ++k) {
+        const int xlo = (int)(box[k].x & 0xffff), xhi = (int)(box[k].x >> 16), ylo = (int)(box[k].y & 0xffff), yhi = (int)(box[k].y >> 16);
+        const bool alive = xlo <= xhi;
+        const bool huge = alive && ((xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE || xhi - xlo + 1 > 32);
+        huge_mask[k] = __ballot_sync(0xffffffffu, huge);
+        if (alive && !huge) {
+            // coarse test: most faces touch no contested pixel; the few that do are queued, so that the costly
+            // part (vertices, exact depths) runs on full warps
+            const int b = (int)((cta0 + k * ZB_THREADS + tid) / a.nf);
+            bool any = false;
+            for (int cy = ylo >> 3; cy <= (yhi >> 3); ++cy)
+                for (int wq = xlo >> 5; wq <= (xhi >> 5); ++wq)
+                    any |= (__ldg(a.zb_coarse + ((size_t)b * a.zb_crows + cy) * a.zb_wpr + wq) & col_mask(wq, xlo, xhi)) != 0u;
+            if (any) s_queue[atomicAdd(&s_n, 1)] = k * ZB_THREADS + tid;
+        }
     }
     __syncthreads();
-    if (tid < s_n) {
-        const long long qidx = cta0 + s_queue[tid];
+    const int nq = s_n;
+    for (int q = tid; q < nq; q += ZB_THREADS) {
+        const long long qidx = cta0 + s_queue[q];
         const int qb = (int)(qidx / a.nf), qf = (int)(qidx % a.nf);
         ZbFace F;
         int qx0, qx1, qy0, qy1;
@@ -486,24 +496,27 @@ k_zb_collect(const RasterArgs a) {
         }
     }
     // huge faces: the whole warp, a lane per (row, word)
-    unsigned todo = __ballot_sync(0xffffffffu, huge);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const long long sidx = __shfl_sync(0xffffffffu, idx, src);
-        const int sb = (int)(sidx / a.nf), sf = (int)(sidx % a.nf);
-        ZbFace G;
-        int gx0, gx1, gy0, gy1;
-        if (!zb_setup(a, sb, sf, G, gx0, gx1, gy0, gy1)) continue;
-        const int w0 = gx0 >> 5, nw = (gx1 >> 5) - w0 + 1;
-        const int items = nw * (gy1 - gy0 + 1);           // (row, word) pairs, a lane each
-        for (int k = lane; k < items; k += 32) {
-            const int y = gy0 + k / nw, wq = w0 + k % nw;
-            unsigned bits = __ldg(a.zb_bitmap + ((size_t)sb * a.R + y) * a.zb_wpr + wq) & col_mask(wq, gx0, gx1);
-            while (bits) {
-                const int x = wq * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                zb_collect_pixel(a, G, grid, sb, x, y);
+#pragma unroll
+    for (int k = 0; k < ZB_COLLECT_PER_THREAD; ++k) {
+        unsigned todo = huge_mask[k];
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const long long sidx = cta0 + k * ZB_THREADS + (tid & ~31) + src;
+            const int sb = (int)(sidx / a.nf), sf = (int)(sidx % a.nf);
+            ZbFace G;
+            int gx0, gx1, gy0, gy1;
+            if (!zb_setup(a, sb, sf, G, gx0, gx1, gy0, gy1)) continue;
+            const int w0 = gx0 >> 5, nw = (gx1 >> 5) - w0 + 1;
+            const int items = nw * (gy1 - gy0 + 1);           // (row, word) pairs, a lane each
+            for (int j = lane; j < items; j += 32) {
+                const int y = gy0 + j / nw, wq = w0 + j % nw;
+                unsigned bits = __ldg(a.zb_bitmap + ((size_t)sb * a.R + y) * a.zb_wpr + wq) & col_mask(wq, gx0, gx1);
+                while (bits) {
+                    const int x = wq * 32 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    zb_collect_pixel(a, G, grid, sb, x, y);
+                }
             }
         }
     }
@@ -678,7 +691,9 @@ k_zb_shade(const RasterArgs a) {
         if (key != ZB_EMPTY) best = (int)(unsigned)(key & 0xffffffffu);
     }
     float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f, bz0 = 0.f, bz1 = 0.f, bz2 = 0.f;
-    if (best >= 0) {
+    // a plain silhouette needs the winner, not its weights: no vertex gather then (three dependent loads less)
+    const bool need_weights = RGB || FULL || (a.flags & FLAG_DEPTH) || a.aux != nullptr;
+    if (best >= 0 && need_weights) {
         int i0 = 3 * best, i1 = 3 * best + 1, i2 = 3 * best + 2;
         if (a.faces) { i0 = __ldg(a.faces + 3 * (size_t)best); i1 = __ldg(a.faces + 3 * (size_t)best + 1); i2 = __ldg(a.faces + 3 * (size_t)best + 2); }
         const float *vb = a.verts + (size_t)b * a.nv * 3;
@@ -727,7 +742,8 @@ cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
     {
         ProfScope p(PROF_ZB_RESOLVE, stream);
         k_zb_slots<<<(unsigned)((words + ZB_THREADS - 1) / ZB_THREADS), ZB_THREADS, 0, stream>>>(a, words);
-        if (face_ctas) k_zb_collect<<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+        if (face_ctas)
+            k_zb_collect<<<(unsigned)((faces + ZB_THREADS * ZB_COLLECT_PER_THREAD - 1) / (ZB_THREADS * ZB_COLLECT_PER_THREAD)), ZB_THREADS, 0, stream>>>(a);
         k_zb_resolve<<<a.sm_count * 4, ZB_THREADS, 0, stream>>>(a, words);
     }
     const bool rgb = (a.flags & FLAG_RGB) != 0, aa = (a.flags & FLAG_AA) != 0;
