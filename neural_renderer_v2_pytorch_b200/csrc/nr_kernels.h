@@ -73,6 +73,7 @@ struct RasterArgs {
     int *zb_head, *zb_pix_of;       // [zb_slot_cap] candidate list head / pixel of every contested pixel
     int4 *zb_nodes;                 // [zb_node_cap] (face, depth, min corner depth, next)
     int zb_slot_cap, zb_node_cap;
+    int zb_row_cost;                // work split of k_zb_faces (set by its launcher)
     // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
     int num_zero;
     void *zero_ptr[4];

@@ -33,6 +33,7 @@
 // If the candidate pool overflows (nrBinStats.overflow; the host grows it for the next call) the lists are
 // unusable and every contested pixel is decided by the reference's own loop over ALL faces of its view, one warp
 // per pixel: slow, exact.
+#include <cstdlib>
 #include "nr_shade.cuh"
 
 namespace nr {
@@ -130,49 +131,145 @@ __device__ __forceinline__ bool zb_setup(const RasterArgs &a, int b, int f, ZbFa
 
 // ---------------------------------------------------------------------------------------------- pass 1
 // A CTA owns 256 consecutive (view, face) pairs.  Their pixel boxes differ wildly (1 .. hundreds of pixels), so
-// "one thread walks its own face" leaves most lanes idle; instead the ROWS of all the boxes of the CTA are laid end
-// to end (prefix sum of the box heights in shared memory) and every thread tests the same number of consecutive
-// (face, row) items, a row per round: the columns of the row in a tight loop, coverage as a bit mask.  The
-// pixels that pass the inside test are compacted into the warp's queue in shared memory (one warp scan per
-// round), and the queue is drained four entries per lane at a time: four cheap depths, four atomicMin issued
-// back to back, then the four checks.  The atomicMin has to RETURN the old minimum, a round trip to L2 of about
-// a microsecond under load: the kernel lives on how many of them it keeps in flight.
-constexpr int ZB_QUEUE = 1536;      // queue entries per warp; a round adds at most 32 lanes x 32 columns
-constexpr int ZB_FLUSH = ZB_QUEUE - 1024;
+// "one thread walks its own face" leaves most lanes idle.  Instead:
+//   * the CTA's faces are ordered by the WIDTH of their pixel box (counting sort in shared memory) and the boxes
+//     are laid end to end in that order (prefix sum of the box areas);
+//   * every thread takes the same number of consecutive box pixels, rounded to whole ROWS, a row per round.
+//     Neighbouring lanes hold rows of (almost) equal width, so the column loop of a round - inside test
+//     (:107-116), coverage as a bit mask - runs with the warp's lanes in step;
+//   * the covered pixels are compacted into the warp's ring in shared memory (one warp scan per round), and the
+//     ring is drained 128 entries at a time, four per lane: four cheap depths, four atomicMin issued back to
+//     back, then the four checks.  The atomicMin has to RETURN the old minimum, a round trip to L2 of about a
+//     microsecond under load: the kernel lives on how many of them it keeps in flight.
+constexpr int ZB_RING = 512;        // ring entries per warp: drained at 128, a round adds at most 32 lanes x 8 columns
+constexpr int ZB_DRAIN = 128;
+constexpr int ZB_COLS = 8;          // columns per round; wider rows take several rounds
+constexpr int ZB_ROW_COST = 4;      // a row costs about as much as this many pixels on top of its own: the threads get equal COSTS
 constexpr int ZB_HUGE = 4096;       // pixel boxes larger than this, or wider than 32 columns, are walked by a whole warp, unqueued
+constexpr int ZB_F_IRREGULAR = 1;   // depths that are not ordinary positive numbers (face_z_regular)
+constexpr int ZB_F_RANGE = 2;       // a depth of this face may come near `near` / `far`: per-pixel range tests
 
 struct ZbFacesShared {
-    // of the CTA's faces: v = x0 y0 x1 y1 x2 y2 | dx10 dy10 dx21 dy21 dx02 dy02 | k0 k1 k2 | iz0 iz1 iz2 (ZbFace)
+    // of the CTA's faces, at their position in width order:
+    // v = x0 y0 x1 y1 x2 y2 | dx10 dy10 dx21 dy21 dx02 dy02 | k0 k1 k2 | iz0 iz1 iz2 (ZbFace)
     float v[18][ZB_THREADS];
     int box[ZB_THREADS];            // xlo | ylo << 16
     int wh[ZB_THREADS];             // width | height << 16 of the pixel box
-    int irregular[ZB_THREADS];      // depths that are not ordinary positive numbers (face_z_regular)
-    int fid[ZB_THREADS], view[ZB_THREADS];
-    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the box heights (dead and huge faces count 0)
-    unsigned hits[ZB_THREADS / 32][ZB_QUEUE];           // per warp: face (local) << 24 | row << 12 | column, inside the box
+    int pixbase[ZB_THREADS];        // index of pixel (xlo, ylo) of the face's view in the z-buffer
+    int fid[ZB_THREADS];            // face | ZB_F_* << 29  (huge faces: the plain face index, see `view`)
+    int view[ZB_THREADS];           // huge faces only
+    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the box costs (rows x (width + a.zb_row_cost)) in width order (huge faces count 0)
+    int start[ZB_THREADS + 1];      // first box pixel of every thread (a row boundary)
+    int hist[40];                   // faces per width (0..31 = width - 1, 32 = huge), then their first positions
     int wsum[ZB_THREADS / 32];
+    unsigned ring[ZB_THREADS / 32][ZB_RING];            // per warp: face position << 24 | row << 12 | column, inside the box
 };
+static_assert(sizeof(ZbFacesShared) <= 48 * 1024, "static shared memory");
 
-// the part of ZbFace the depth of a covered pixel needs (zb_prepare)
-__device__ __forceinline__ void zb_face_from_shared(const ZbFacesShared &sh, int i, ZbFace &f) {
+// ... the whole face (huge faces)
+__device__ __forceinline__ void zb_whole_face_from_shared(const ZbFacesShared &sh, int i, ZbFace &f) {
     f.dx10 = sh.v[6][i]; f.dy10 = sh.v[7][i]; f.dx21 = sh.v[8][i]; f.dy21 = sh.v[9][i]; f.dx02 = sh.v[10][i]; f.dy02 = sh.v[11][i];
     f.k0 = sh.v[12][i]; f.k1 = sh.v[13][i]; f.k2 = sh.v[14][i];
     f.iz0 = sh.v[15][i]; f.iz1 = sh.v[16][i]; f.iz2 = sh.v[17][i];
-    f.zreg = sh.irregular[i] == 0;
-    f.fid = sh.fid[i];
-}
-// ... and the whole of it (huge faces)
-__device__ __forceinline__ void zb_whole_face_from_shared(const ZbFacesShared &sh, int i, ZbFace &f) {
-    zb_face_from_shared(sh, i, f);
+    f.zreg = (sh.fid[i] & (ZB_F_IRREGULAR << 29)) == 0;
+    f.fid = sh.fid[i] & 0x1fffffff;
     f.x0 = sh.v[0][i]; f.y0 = sh.v[1][i]; f.x1 = sh.v[2][i]; f.y1 = sh.v[3][i]; f.x2 = sh.v[4][i]; f.y2 = sh.v[5][i];
     f.z0 = f.z1 = f.z2 = 0.f;       // (the cheap depth uses the reciprocals)
 }
 
+// contested-pixel flag from the z-buffer index of the pixel
+__device__ __forceinline__ void zb_flag_pix(const RasterArgs &a, unsigned pix) {
+    if ((a.R & 31) == 0) {
+        atomicOr(a.zb_bitmap + (pix >> 5), 1u << (pix & 31));
+    } else {
+        const unsigned rowi = pix / (unsigned)a.R, x = pix - rowi * (unsigned)a.R;      // rowi = view * R + y
+        atomicOr(a.zb_bitmap + (size_t)rowi * a.zb_wpr + (x >> 5), 1u << (x & 31));
+    }
+}
+
+// Ring entries [head, head + n) of the warp (n <= 128): cheap depth, atomicMin, check; four per lane in flight.
 template <bool POW2>
-__global__ void __launch_bounds__(ZB_THREADS)
+__device__ __forceinline__ void zb_drain(const RasterArgs &a, const ZbFacesShared &sh, const unsigned *ring, int head, int n, int lane,
+                                         const PixGrid &grid) {
+    const int R = a.R;
+    float zf[4];
+    unsigned pix[4];
+    int fv[4];
+    bool go[4];
+    unsigned long long old[4];
+    unsigned flags = 0u;                // contested pixels among my four
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int h = k * 32 + lane;
+        go[k] = false;
+        if (h < n) {
+            const unsigned hc = ring[(head + h) & (ZB_RING - 1)];
+            const int li = hc >> 24, col = (int)(hc & 0xfff), row = (int)((hc >> 12) & 0xfff);
+            const int bx = sh.box[li];
+            const int x = (bx & 0xffff) + col, y = (int)((unsigned)bx >> 16) + row;
+            pix[k] = (unsigned)(sh.pixbase[li] + row * R + col);
+            const int fl = sh.fid[li];
+            fv[k] = fl & 0x1fffffff;
+            const float xp = POW2 ? __fmul_rn((float)(2 * x + 1 - R), grid.invR) : pix_center(x, R);
+            const float yp = POW2 ? __fmul_rn((float)(2 * y + 1 - R), grid.invR) : pix_center(y, R);
+            // zb_weights() / zb_prepare() from the shared copy of the face
+            const float w0 = __fadd_rn(__fmaf_rn(yp, sh.v[8][li], __fmul_rn(xp, -sh.v[9][li])), sh.v[12][li]);
+            const float w1 = __fadd_rn(__fmaf_rn(yp, sh.v[10][li], __fmul_rn(xp, -sh.v[11][li])), sh.v[13][li]);
+            const float w2 = __fadd_rn(__fmaf_rn(yp, sh.v[6][li], __fmul_rn(xp, -sh.v[7][li])), sh.v[14][li]);
+            // weights_one_sign(), branch-free (a NaN weight makes the sum a NaN)
+            const float ws = __fadd_rn(__fadd_rn(w0, w1), w2);
+            const bool regular = ((fminf(w0, fminf(w1, w2)) >= 0.f) | (fmaxf(w0, fmaxf(w1, w2)) <= 0.f)) & (ws == ws) &
+                                 ((fl & (ZB_F_IRREGULAR << 29)) == 0);
+            zf[k] = fast_zp(w0, w1, w2, sh.v[15][li], sh.v[16][li], sh.v[17][li]);
+            go[k] = regular;
+            bool flag = !regular;               // irregular: the exact scan decides this pixel
+            if (regular && (fl & (ZB_F_RANGE << 29))) {
+                // (zb_prepare) :140-142 rejects zp <= near and zp >= far; a depth in (far - delta, far) is valid but can
+                // never pass the z-test against the initial minimum `far`, nor against a smaller one
+                const float m = FAST_Z_REL * zf[k], top = a.far_plane - a.delta;
+                if (zf[k] < a.near_plane - m || zf[k] > top + m) go[k] = false;
+                else if (!(zf[k] > a.near_plane + m && zf[k] < top - m && zf[k] * 1e-6f < a.delta)) {      // (NaN: contested)
+                    go[k] = false;
+                    flag = true;
+                }
+            }
+            if (flag) flags |= 1u << k;
+        }
+    }
+    if (__any_sync(0xffffffffu, flags != 0u)) {      // rare
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (flags & (1u << k)) zb_flag_pix(a, pix[k]);
+        flags = 0u;
+    }
+    if (a.flags & (1 << 28)) {        // experiment: no atomics
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (go[k] && zf[k] == 12345.678f) zb_flag_pix(a, pix[k] + fv[k]);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (go[k]) old[k] = atomicMin(a.zbuf + pix[k], zb_key(zf[k], fv[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (go[k] && old[k] != ZB_EMPTY) {
+            // (zb_check) within the hysteresis (plus both error bounds and the rounding of depth_min - delta) of the
+            // minimum of this moment: order may matter
+            const float zo = __uint_as_float((unsigned)(old[k] >> 32));
+            if (fabsf(zf[k] - zo) < a.delta + 2.5f * FAST_Z_REL * fmaxf(zf[k], zo)) flags |= 1u << k;
+        }
+    if (__any_sync(0xffffffffu, flags != 0u)) {      // rare
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (flags & (1u << k)) zb_flag_pix(a, pix[k]);
+    }
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(ZB_THREADS, 4)
 k_zb_faces(const RasterArgs a) {
-    extern __shared__ __align__(16) unsigned char zb_dynamic_smem[];
-    ZbFacesShared &sh = *reinterpret_cast<ZbFacesShared *>(zb_dynamic_smem);
+    __shared__ ZbFacesShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int R = a.R;
     const PixGrid grid(R);
@@ -180,36 +277,70 @@ k_zb_faces(const RasterArgs a) {
     const long long idx = (long long)blockIdx.x * ZB_THREADS + tid;
     const bool in = idx < (long long)a.B * a.nf;
     const int b = in ? (int)(idx / a.nf) : 0, f = in ? (int)(idx % a.nf) : 0;
+    if (tid < 40) sh.hist[tid] = 0;
+    __syncthreads();
     // ---- per-face setup (rasterize.py:232, :94-104, :118-121)
-    int area = 0, rows_mine = 0;
-    bool huge = false;
+    int key, rank;
+    ZbFace F;
+    int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
+    bool alive;
     {
         FaceRec r;
-        int xlo = 1, xhi = 0, ylo = 1, yhi = 0;
-        const bool alive = in && make_face_record(a.verts + (size_t)b * a.nv * 3, a.faces, f, a.nv, R, (a.flags & FLAG_BACKSIDE) ? 1 : 0,
-                                                  r, xlo, xhi, ylo, yhi, a.hdr);
-        const int w = xhi - xlo + 1, h = yhi - ylo + 1;
-        if (alive) area = w * h;
-        huge = area > ZB_HUGE || (alive && w > 32);
-        rows_mine = (alive && !huge) ? h : 0;
+        alive = in && make_face_record(a.verts + (size_t)b * a.nv * 3, a.faces, f, a.nv, R, (a.flags & FLAG_BACKSIDE) ? 1 : 0,
+                                       r, xlo, xhi, ylo, yhi, a.hdr);
         // the exact pixel box for the collect pass, which then needs no vertices for faces that touch nothing contested
         if (in) a.zb_box[idx] = alive ? make_uint2((unsigned)xlo | ((unsigned)xhi << 16), (unsigned)ylo | ((unsigned)yhi << 16))
                                       : make_uint2(DEAD_BBOX, 0u);
-        ZbFace F;
         zb_face_from_record(r, f, F);
-        sh.v[0][tid] = F.x0; sh.v[1][tid] = F.y0; sh.v[2][tid] = F.x1; sh.v[3][tid] = F.y1; sh.v[4][tid] = F.x2; sh.v[5][tid] = F.y2;
-        sh.v[6][tid] = F.dx10; sh.v[7][tid] = F.dy10; sh.v[8][tid] = F.dx21; sh.v[9][tid] = F.dy21; sh.v[10][tid] = F.dx02; sh.v[11][tid] = F.dy02;
-        sh.v[12][tid] = F.k0; sh.v[13][tid] = F.k1; sh.v[14][tid] = F.k2;
-        sh.v[15][tid] = F.iz0; sh.v[16][tid] = F.iz1; sh.v[17][tid] = F.iz2;
-        sh.box[tid] = alive ? (xlo | (ylo << 16)) : 0;
-        sh.wh[tid] = alive ? (w | (h << 16)) : 0;
-        sh.irregular[tid] = F.zreg ? 0 : 1;
-        sh.fid[tid] = f;
-        sh.view[tid] = b;
     }
-    // ---- the boxes end to end
+    const int w = xhi - xlo + 1, h = yhi - ylo + 1;
+    const bool huge = alive && (w * h > ZB_HUGE || w > 32);
+    // ---- width order: position = first position of my width + my rank among the faces of that width
+    key = huge ? 32 : w - 1;
+    rank = alive ? atomicAdd(&sh.hist[key], 1) : 0;
+    __syncthreads();
+    if (wid == 0) {
+        const int c = sh.hist[lane];
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int nh = sh.hist[32];
+        __syncwarp();
+        sh.hist[lane] = inc - c;
+        if (lane == 31) {
+            sh.hist[32] = inc;              // number of faces that go through the rows = first position of the huge ones
+            sh.hist[33] = inc + nh;         // live faces
+        }
+    }
+    __syncthreads();
+    const int n_rows = sh.hist[32], n_live = sh.hist[33];
+    if (alive) {
+        const int pos = sh.hist[key] + rank;
+        sh.v[0][pos] = F.x0; sh.v[1][pos] = F.y0; sh.v[2][pos] = F.x1; sh.v[3][pos] = F.y1; sh.v[4][pos] = F.x2; sh.v[5][pos] = F.y2;
+        sh.v[6][pos] = F.dx10; sh.v[7][pos] = F.dy10; sh.v[8][pos] = F.dx21; sh.v[9][pos] = F.dy21; sh.v[10][pos] = F.dx02; sh.v[11][pos] = F.dy02;
+        sh.v[12][pos] = F.k0; sh.v[13][pos] = F.k1; sh.v[14][pos] = F.k2;
+        sh.v[15][pos] = F.iz0; sh.v[16][pos] = F.iz1; sh.v[17][pos] = F.iz2;
+        sh.box[pos] = xlo | (ylo << 16);
+        sh.wh[pos] = w | (h << 16);
+        sh.pixbase[pos] = (b * R + ylo) * R + xlo;
+        // A regular face's cheap depths lie in [min z, max z] up to FAST_Z_REL (same-sign weights): when that interval
+        // is clear of near and of far - delta by a wide margin, zb_prepare's range tests pass for every pixel
+        const float zmin = fminf(F.z0, fminf(F.z1, F.z2)), zmax = fmaxf(F.z0, fmaxf(F.z1, F.z2));
+        const float lo = zmin * (1.f - 8e-6f), hi = zmax * (1.f + 8e-6f), top = a.far_plane - a.delta;
+        const float cmax = fmaxf(fmaxf(fmaxf(fabsf(F.x0), fabsf(F.x1)), fmaxf(fabsf(F.x2), fabsf(F.y0))), fmaxf(fabsf(F.y1), fabsf(F.y2)));
+        const bool clear = F.zreg && lo > a.near_plane + 8e-6f * hi && hi < top - 8e-6f * hi && hi * 1.001e-6f < a.delta &&
+                           cmax < 1e6f;         // (finite weights of ordinary size)
+        sh.fid[pos] = f | (((F.zreg ? 0 : ZB_F_IRREGULAR) | (clear ? 0 : ZB_F_RANGE)) << 29);
+        sh.view[pos] = b;
+    }
+    __syncthreads();
+    // ---- the boxes end to end, in width order
     {
-        const int my = rows_mine;
+        const int wh_ = tid < n_rows ? sh.wh[tid] : 0;
+        const int my = tid < n_rows ? ((wh_ & 0xffff) + a.zb_row_cost) * (int)((unsigned)wh_ >> 16) : 0;
         int inc = my;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -226,113 +357,110 @@ k_zb_faces(const RasterArgs a) {
         if (tid == ZB_THREADS - 1) sh.pre[ZB_THREADS] = base + inc;
         __syncthreads();
     }
-    const int W = sh.pre[ZB_THREADS];
-    const int chunk = (W + ZB_THREADS - 1) / ZB_THREADS;
-    int pos = min(tid * chunk, W);
-    const int end = min(pos + chunk, W);
-    // ---- my first item: face i = the one with pre[i] <= pos < pre[i + 1], then the row inside its box
-    int i = 0, r = 0, nxt = 0, fw = 1, fx = 0, fy = 0;
-    float x0 = 0.f, y0 = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, dx10 = 0.f, dy10 = 0.f, dx21 = 0.f, dy21 = 0.f, dx02 = 0.f, dy02 = 0.f;
-    auto load_face = [&](int j) {
-        x0 = sh.v[0][j]; y0 = sh.v[1][j]; x1 = sh.v[2][j]; y1 = sh.v[3][j]; x2 = sh.v[4][j]; y2 = sh.v[5][j];
-        dx10 = sh.v[6][j]; dy10 = sh.v[7][j]; dx21 = sh.v[8][j]; dy21 = sh.v[9][j]; dx02 = sh.v[10][j]; dy02 = sh.v[11][j];
-        fw = sh.wh[j] & 0xffff;
-        fx = sh.box[j] & 0xffff;
-        fy = (int)((unsigned)sh.box[j] >> 16);
-        nxt = sh.pre[j + 1];
-    };
-    if (pos < end) {
-        int lo = 0, hi = ZB_THREADS;            // first j with pre[j] > pos (pre[256] = W > pos)
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sh.pre[mid] > pos) hi = mid; else lo = mid + 1;
+    const int total = sh.pre[ZB_THREADS];
+    // ---- my share: `chunk` box pixels from the first row that starts at or behind pixel tid * chunk
+    int p = 0, row = 0;
+    {
+        const int chunk = (total + ZB_THREADS - 1) / ZB_THREADS;
+        const int t0 = min(tid * chunk, total);
+        int st = total;
+        if (t0 < total) {
+            int lo = 0, hi = n_rows;                // first j with pre[j] > t0 (pre[n_rows] = total > t0)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sh.pre[mid] > t0) hi = mid; else lo = mid + 1;
+            }
+            p = lo - 1;
+            const int wh_ = sh.wh[p], fw_ = (wh_ & 0xffff) + a.zb_row_cost;
+            row = (t0 - sh.pre[p] + fw_ - 1) / fw_;
+            if (row == (int)((unsigned)wh_ >> 16)) {
+                ++p;
+                row = 0;
+            }
+            st = sh.pre[p] + row * (p < n_rows ? (sh.wh[p] & 0xffff) + a.zb_row_cost : 0);
         }
-        i = lo - 1;
-        load_face(i);
-        r = pos - sh.pre[i];
+        sh.start[tid] = st;
+        if (tid == 0) sh.start[ZB_THREADS] = total;
+        __syncthreads();
     }
-    // The warps run on their own from here: the rows of a warp's 32 threads go through the warp's own queue.
-    unsigned *queue = sh.hits[wid];
-    const int rounds = (wid * 32 * chunk < W) ? chunk : 0;
-    int H = 0;                                                  // queue fill, warp-uniform
-    for (int round = 0; round < rounds; ++round) {
-        // ---- phase A: one row per lane, inside tests (:107-116) over its columns, hits into the queue
-        unsigned mask = 0u, code = 0u;
-        if (pos < end) {
-            const float yp = center(fy + r);
-            const float a1 = __fsub_rn(yp, y0), a2 = __fsub_rn(yp, y1), a3 = __fsub_rn(yp, y2);
-            for (int c = 0; c < fw; ++c) {
-                const float xp = center(fx + c);
+    int rem = sh.start[tid + 1] - sh.start[tid];          // cost of this thread's rows
+    if (a.flags & (1 << 29)) return;  // experiment: setup only
+    // The warps run on their own from here.
+    unsigned *ring = sh.ring[wid];
+    const float step = 2.f * grid.invR;              // POW2: centre(i + 1) = centre(i) + 2 / R, exactly
+    int head = 0, tail = 0;                                     // warp-uniform
+    while (__any_sync(0xffffffffu, rem > 0)) {
+        // ---- one row per lane
+        const bool act = rem > 0;
+        const int j = act ? p : 0;
+        const int wh_ = sh.wh[j], bx = sh.box[j];
+        const int fw = act ? (wh_ & 0xffff) : 0, fh = (int)((unsigned)wh_ >> 16);
+        const int fx = bx & 0xffff, fy = (int)((unsigned)bx >> 16);
+        const float x0 = sh.v[0][j], x1 = sh.v[2][j], x2 = sh.v[4][j];
+        const float dx10 = sh.v[6][j], dy10 = sh.v[7][j], dx21 = sh.v[8][j], dy21 = sh.v[9][j], dx02 = sh.v[10][j], dy02 = sh.v[11][j];
+        const float yp = center(fy + row);
+        const float a1 = __fsub_rn(yp, sh.v[1][j]), a2 = __fsub_rn(yp, sh.v[3][j]), a3 = __fsub_rn(yp, sh.v[5][j]);
+        const unsigned coderow = ((unsigned)j << 24) | ((unsigned)row << 12);
+        const int wmax = __reduce_max_sync(0xffffffffu, fw);
+        float xp = center(fx);
+        for (int c0 = 0; c0 < wmax; c0 += ZB_COLS) {
+            // inside tests (:107-116) over (at most) eight columns, coverage as a bit mask
+            const int kend = min(ZB_COLS, wmax - c0);
+            unsigned mask = 0u;               // bit (kend - 1 - k) = column c0 + k
+#pragma unroll 2
+            for (int k = 0; k < kend; ++k) {
                 const float c1 = __fmaf_rn(a1, dx10, -__fmul_rn(dy10, __fsub_rn(xp, x0)));
                 const float c2 = __fmaf_rn(a2, dx21, -__fmul_rn(dy21, __fsub_rn(xp, x1)));
                 const float c3 = __fmaf_rn(a3, dx02, -__fmul_rn(dy02, __fsub_rn(xp, x2)));
-                if (!((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f))) mask |= 1u << c;
+                const bool hit = !((__fmul_rn(c1, c2) < 0.f) | (__fmul_rn(c2, c3) < 0.f));
+                mask = mask + mask + (hit ? 1u : 0u);
+                xp = POW2 ? __fadd_rn(xp, step) : center(fx + c0 + k + 1);
             }
-            code = ((unsigned)i << 24) | ((unsigned)r << 12);
-            ++pos;
-            ++r;
-            if (pos == nxt && pos < end) {
-                do ++i; while (sh.pre[i + 1] == sh.pre[i]);       // (faces without rows)
-                load_face(i);
-                r = 0;
+            // columns beyond MY row (inactive lanes: all)
+            const int over = c0 + kend - fw;
+            if (over > 0) mask = over >= kend ? 0u : (mask >> over) << over;
+            // exclusive scan of the hit counts over the lanes: where this lane's hits go
+            const int cnt = __popc(mask);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int slot = tail + inc - cnt;
+            const unsigned code = coderow + (unsigned)(c0 + kend - 1);
+            while (mask) {
+                ring[(slot++) & (ZB_RING - 1)] = code - (unsigned)(__ffs(mask) - 1);
+                mask &= mask - 1;
+            }
+            tail += __shfl_sync(0xffffffffu, inc, 31);
+            if (a.flags & (1 << 30)) head = tail;     // experiment: no drain
+            while (tail - head >= ZB_DRAIN) {
+                __syncwarp();
+                zb_drain<POW2>(a, sh, ring, head, ZB_DRAIN, lane, grid);
+                __syncwarp();
+                head += ZB_DRAIN;
             }
         }
-        // exclusive scan of the hit counts over the lanes: where this lane's hits go
-        const int cnt = __popc(mask);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        int slot = H + inc - cnt;
-        while (mask) {
-            queue[slot++] = code | (unsigned)(__ffs(mask) - 1);
-            mask &= mask - 1;
-        }
-        H += __shfl_sync(0xffffffffu, inc, 31);
-        if (H <= ZB_FLUSH && round + 1 < rounds) continue;
-        __syncwarp();
-        // ---- phase B: the queue, four entries per lane at a time
-        for (int hb = 0; hb < H; hb += 4 * 32) {
-            float zf[4];
-            int pxy[4], fv[4], bv[4];
-            bool go[4];
-            unsigned long long old[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int h = hb + k * 32 + lane;
-                go[k] = false;
-                if (h < H) {
-                    const unsigned hc = queue[h];
-                    const int li = hc >> 24;
-                    ZbFace F;
-                    zb_face_from_shared(sh, li, F);
-                    const int x = (sh.box[li] & 0xffff) + (int)(hc & 0xfff), y = (int)((unsigned)sh.box[li] >> 16) + (int)((hc >> 12) & 0xfff);
-                    bv[k] = sh.view[li];
-                    fv[k] = F.fid;
-                    pxy[k] = x | (y << 16);
-                    go[k] = zb_prepare(a, F, center(x), center(y), bv[k], x, y, zf[k]);
-                }
+        // ---- next row
+        if (act) {
+            rem -= fw + a.zb_row_cost;
+            if (++row == fh) {
+                row = 0;
+                ++p;
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (go[k]) old[k] = atomicMin(a.zbuf + ((size_t)bv[k] * R + (pxy[k] >> 16)) * R + (pxy[k] & 0xffff), zb_key(zf[k], fv[k]));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (go[k]) zb_check(a, zf[k], old[k], bv[k], pxy[k] & 0xffff, pxy[k] >> 16);
         }
-        H = 0;
-        __syncwarp();
     }
-    // ---- huge faces: the whole warp walks the box of one of its lanes' faces, a lane per pixel: the lanes form
-    // a (32 / wb) x wb patch, wb = the box width rounded up to a power of two (32 at most), that steps over the
-    // box; two patches per round keep two atomics per lane in flight
-    unsigned todo = __ballot_sync(0xffffffffu, huge);
-    int nhuge = __popc(todo);
-    while (todo) {
-        const int src = (wid << 5) + __ffs(todo) - 1;
-        todo &= todo - 1;
+    while (tail > head) {
+        const int nd = min(tail - head, ZB_DRAIN);
+        __syncwarp();
+        zb_drain<POW2>(a, sh, ring, head, nd, lane, grid);
+        head += nd;
+    }
+    // ---- huge faces: the whole warp walks the box of one face, a lane per pixel: the lanes form a (32 / wb) x wb
+    // patch, wb = the box width rounded up to a power of two (32 at most), that steps over the box; two patches
+    // per round keep two atomics per lane in flight.  Warp k takes the huge faces k, k + 8, ...
+    for (int src = n_rows + wid; src < n_live; src += ZB_THREADS / 32) {
         ZbFace G;
         zb_whole_face_from_shared(sh, src, G);
         const int sb = sh.view[src], gx0 = sh.box[src] & 0xffff, gy0 = (int)((unsigned)sh.box[src] >> 16);
@@ -353,8 +481,8 @@ k_zb_faces(const RasterArgs a) {
                     py[k] = yb + k * rows + lr;
                     go[k] = false;
                     if (x <= gx1 && py[k] <= gy1) {
-                        const float xp = center(x), yp = center(py[k]);
-                        if (zb_inside(G, xp, yp)) go[k] = zb_prepare(a, G, xp, yp, sb, x, py[k], zf[k]);
+                        const float xq = center(x), yq = center(py[k]);
+                        if (zb_inside(G, xq, yq)) go[k] = zb_prepare(a, G, xq, yq, sb, x, py[k], zf[k]);
                     }
                 }
 #pragma unroll
@@ -367,7 +495,7 @@ k_zb_faces(const RasterArgs a) {
         }
     }
     // statistics for the host: a mesh with many such faces belongs to the tile pipeline
-    if (nhuge && lane == 0) atomicAdd(&a.hdr->max_tile_faces, nhuge);
+    if (tid == 0 && n_live > n_rows) atomicAdd(&a.hdr->max_tile_faces, n_live - n_rows);
 }
 
 // ---------------------------------------------------------------------------------------------- pass 2
@@ -713,7 +841,16 @@ k_zb_shade(const RasterArgs a) {
     }
 }
 
-cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
+cudaError_t launch_raster_zbuf(const RasterArgs &a_in, cudaStream_t stream) {
+    RasterArgs a = a_in;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("NR_ZB_DEBUG"); dbg = e ? atoi(e) : 0; }
+        a.flags |= (dbg & 7) << 28;
+        static int rc = -1;
+        if (rc < 0) { const char *e = getenv("NR_ZB_ROW_COST"); rc = e ? atoi(e) : ZB_ROW_COST; }
+        a.zb_row_cost = rc;
+    }
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     const long long faces = (long long)a.B * a.nf, words = (long long)a.B * a.R * a.zb_wpr;
     const long long plane = (long long)a.B * a.R * a.R;
@@ -728,16 +865,8 @@ cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
     const unsigned face_ctas = (unsigned)((faces + ZB_THREADS - 1) / ZB_THREADS);
     if (face_ctas) {
         ProfScope p(PROF_ZB_FACES, stream);
-        static bool attr_set[64] = {false};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-            if ((e = cudaFuncSetAttribute(k_zb_faces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbFacesShared))) != cudaSuccess) return e;
-            if ((e = cudaFuncSetAttribute(k_zb_faces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZbFacesShared))) != cudaSuccess) return e;
-            attr_set[dev] = true;
-        }
-        if ((a.R & (a.R - 1)) == 0) k_zb_faces<true><<<face_ctas, ZB_THREADS, sizeof(ZbFacesShared), stream>>>(a);
-        else k_zb_faces<false><<<face_ctas, ZB_THREADS, sizeof(ZbFacesShared), stream>>>(a);
+        if ((a.R & (a.R - 1)) == 0) k_zb_faces<true><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
+        else k_zb_faces<false><<<face_ctas, ZB_THREADS, 0, stream>>>(a);
     }
     {
         ProfScope p(PROF_ZB_RESOLVE, stream);
