@@ -562,24 +562,60 @@ __device__ __forceinline__ void zb_collect_pixel(const RasterArgs &a, const ZbFa
 }
 
 constexpr int ZB_COLLECT_PER_THREAD = 4;        // faces per thread: four box loads (and the coarse lookups behind them) in flight
+constexpr int ZB_COLLECT_FACES = ZB_THREADS * ZB_COLLECT_PER_THREAD;
+constexpr int ZB_PAIR_CAP = 2048;               // (face, contested pixel) pairs of a CTA gathered in shared memory; more are taken one by one
 
+// Face f of view b for the exact depth: its vertices and what zb_inside / zb_weights need.  The face-level tests
+// were k_zb_faces' business: only faces with a live pixel box get here.
+__device__ __forceinline__ void zb_gather(const RasterArgs &a, int b, int f, ZbFace &F) {
+    int i0 = 3 * f, i1 = 3 * f + 1, i2 = 3 * f + 2;
+    if (a.faces) { i0 = __ldg(a.faces + 3 * (size_t)f); i1 = __ldg(a.faces + 3 * (size_t)f + 1); i2 = __ldg(a.faces + 3 * (size_t)f + 2); }
+    const float *vb = a.verts + (size_t)b * a.nv * 3;
+    FaceRec r;
+    r.q0 = make_float4(__ldg(vb + 3 * (size_t)i0), __ldg(vb + 3 * (size_t)i0 + 1), __ldg(vb + 3 * (size_t)i0 + 2), __ldg(vb + 3 * (size_t)i1));
+    r.q1 = make_float4(__ldg(vb + 3 * (size_t)i1 + 1), __ldg(vb + 3 * (size_t)i1 + 2), __ldg(vb + 3 * (size_t)i2), __ldg(vb + 3 * (size_t)i2 + 1));
+    r.q2 = make_float4(__ldg(vb + 3 * (size_t)i2 + 2), 0.f, 0.f, 0.f);
+    zb_face_from_record(r, f, F);
+}
+
+// Three steps, each on full warps: (1) a thread per face: pixel box (as pass 1 found it) against the coarse
+// bitmap - most faces touch no contested pixel; (2) EIGHT lanes per face that passed, a row of its box each,
+// against the bitmap itself: every contested pixel inside the box becomes a (face, pixel) pair; (3) a thread per
+// pair: vertices, inside test, the reference's depth, the pixel's list.
 __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_collect(const RasterArgs a) {
-    __shared__ int s_queue[ZB_THREADS * ZB_COLLECT_PER_THREAD];
-    __shared__ int s_n;
+    __shared__ int s_queue[ZB_COLLECT_FACES];
+    __shared__ uint2 s_qbox[ZB_COLLECT_FACES];
+    __shared__ int2 s_pairs[ZB_PAIR_CAP];
+    __shared__ int s_n, s_np;
     if (a.hdr->zb_slots == 0) return;                     // nothing contested (uniform over the grid)
     const int tid = threadIdx.x, lane = tid & 31;
     const long long total = (long long)a.B * a.nf;
-    const long long cta0 = (long long)blockIdx.x * (ZB_THREADS * ZB_COLLECT_PER_THREAD);
-    const PixGrid grid(a.R);
-    // bits of columns [c0, c1] in bitmap word wq
-    auto col_mask = [](int wq, int c0, int c1) -> unsigned {
-        const int lo = max(c0 - wq * 32, 0), hi = min(c1 - wq * 32, 31);
-        return (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+    const long long cta0 = (long long)blockIdx.x * ZB_COLLECT_FACES;
+    const int b0 = (int)(cta0 / a.nf);                    // view of the CTA's first face
+    const unsigned f0 = (unsigned)(cta0 - (long long)b0 * a.nf);
+    const bool two_views = a.nf >= ZB_COLLECT_FACES;      // the CTA's faces belong to at most two views
+    auto view_face = [&](int slot, int &b, int &f) {      // slot = position in the CTA's range of (view, face) pairs
+        const unsigned o = f0 + (unsigned)slot;
+        const unsigned q = two_views ? (o >= (unsigned)a.nf ? 1u : 0u) : o / (unsigned)a.nf;
+        b = b0 + (int)q;
+        f = (int)(o - q * (unsigned)a.nf);
     };
-    if (tid == 0) s_n = 0;
+    const PixGrid grid(a.R);
+    // A box of at most 32 columns [c0, c1] lies in bitmap words w0 = c0 >> 5 and (perhaps) w0 + 1: its bits there
+    auto word_masks = [](int c0, int c1, unsigned &m0, unsigned &m1) {
+        const int w0 = c0 >> 5;
+        m0 = 0xffffffffu << (c0 & 31);
+        m1 = 0u;
+        if ((c1 >> 5) == w0) m0 &= 0xffffffffu >> (31 - (c1 & 31));
+        else m1 = 0xffffffffu >> (31 - (c1 & 31));
+    };
+    if (tid == 0) {
+        s_n = 0;
+        s_np = 0;
+    }
     __syncthreads();
-    // the faces' pixel boxes as pass 1 found them
+    // ---- (1) the faces' pixel boxes as pass 1 found them, against the coarse bitmap
     uint2 box[ZB_COLLECT_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < ZB_COLLECT_PER_THREAD; ++k) {
@@ -594,35 +630,78 @@ k_zb_collect(const RasterArgs a) {
         const bool huge = alive && ((xhi - xlo + 1) * (yhi - ylo + 1) > ZB_HUGE || xhi - xlo + 1 > 32);
         huge_mask[k] = __ballot_sync(0xffffffffu, huge);
         if (alive && !huge) {
-            // coarse test: most faces touch no contested pixel; the few that do are queued, so that the costly
-            // part (vertices, exact depths) runs on full warps
-            const int b = (int)((cta0 + k * ZB_THREADS + tid) / a.nf);
-            bool any = false;
-            for (int cy = ylo >> 3; cy <= (yhi >> 3); ++cy)
-                for (int wq = xlo >> 5; wq <= (xhi >> 5); ++wq)
-                    any |= (__ldg(a.zb_coarse + ((size_t)b * a.zb_crows + cy) * a.zb_wpr + wq) & col_mask(wq, xlo, xhi)) != 0u;
-            if (any) s_queue[atomicAdd(&s_n, 1)] = k * ZB_THREADS + tid;
+            int b, f;
+            view_face(k * ZB_THREADS + tid, b, f);
+            unsigned m0, m1;
+            word_masks(xlo, xhi, m0, m1);
+            const unsigned *cb = a.zb_coarse + ((size_t)b * a.zb_crows + (ylo >> 3)) * a.zb_wpr + (xlo >> 5);
+            unsigned any = 0u;
+            for (int cy = ylo >> 3; cy <= (yhi >> 3); ++cy, cb += a.zb_wpr) {
+                any |= __ldg(cb) & m0;
+                if (m1) any |= __ldg(cb + 1) & m1;
+            }
+            if (any) {
+                const int q = atomicAdd(&s_n, 1);
+                s_queue[q] = k * ZB_THREADS + tid;
+                s_qbox[q] = box[k];
+            }
         }
     }
     __syncthreads();
+    // ---- (2) the rows of the boxes that passed: lane group g of 8 takes face g, g + 32, ..., its lanes the rows
     const int nq = s_n;
-    for (int q = tid; q < nq; q += ZB_THREADS) {
-        const long long qidx = cta0 + s_queue[q];
-        const int qb = (int)(qidx / a.nf), qf = (int)(qidx % a.nf);
-        ZbFace F;
-        int qx0, qx1, qy0, qy1;
-        if (zb_setup(a, qb, qf, F, qx0, qx1, qy0, qy1)) {
-            for (int y = qy0; y <= qy1; ++y)
-                for (int wq = qx0 >> 5; wq <= (qx1 >> 5); ++wq) {
-                    unsigned bits = __ldg(a.zb_bitmap + ((size_t)qb * a.R + y) * a.zb_wpr + wq) & col_mask(wq, qx0, qx1);
-                    while (bits) {
-                        const int x = wq * 32 + __ffs(bits) - 1;
-                        bits &= bits - 1;
+#ifdef NR_ZB_STATS
+    if (tid == 0) atomicAdd(&a.hdr->zb_work[1], nq);
+#endif
+    for (int q = tid >> 3; q < nq; q += ZB_THREADS / 8) {
+        const int slot = s_queue[q];
+        const uint2 bx = s_qbox[q];
+        const int qx0 = (int)(bx.x & 0xffff), qx1 = (int)(bx.x >> 16), qy0 = (int)(bx.y & 0xffff), qy1 = (int)(bx.y >> 16);
+        int qb, qf;
+        view_face(slot, qb, qf);
+        unsigned m0, m1;
+        word_masks(qx0, qx1, m0, m1);
+        const int w0 = qx0 >> 5;
+        const unsigned *bm = a.zb_bitmap + (size_t)qb * a.R * a.zb_wpr + w0;
+        for (int y = qy0 + (tid & 7); y <= qy1; y += 8) {
+            const unsigned *rowp = bm + (size_t)y * a.zb_wpr;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !m1) break;
+                unsigned bits = __ldg(rowp + h) & (h ? m1 : m0);
+                while (bits) {
+                    const int x = (w0 + h) * 32 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int n = atomicAdd(&s_np, 1);
+                    if (n < ZB_PAIR_CAP) {
+                        s_pairs[n] = make_int2(slot, x | (y << 16));
+                    } else {                              // (a CTA whose faces sit on thousands of contested pixels)
+                        ZbFace F;
+                        zb_gather(a, qb, qf, F);
                         zb_collect_pixel(a, F, grid, qb, x, y);
                     }
                 }
+            }
         }
     }
+    __syncthreads();
+    // ---- (3) the pairs
+    const int np = min(s_np, ZB_PAIR_CAP);
+#ifdef NR_ZB_STATS
+    if (tid == 0) atomicAdd(&a.hdr->zb_work[2], s_np);
+#endif
+    for (int i = tid; i < np; i += ZB_THREADS) {
+        const int2 pr = s_pairs[i];
+        int pb, pf;
+        view_face(pr.x, pb, pf);
+        ZbFace F;
+        zb_gather(a, pb, pf, F);
+        zb_collect_pixel(a, F, grid, pb, pr.y & 0xffff, pr.y >> 16);
+    }
+    auto col_mask = [](int wq, int c0, int c1) -> unsigned {
+        const int lo = max(c0 - wq * 32, 0), hi = min(c1 - wq * 32, 31);
+        return (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+    };
     // huge faces: the whole warp, a lane per (row, word)
 #pragma unroll
     for (int k = 0; k < ZB_COLLECT_PER_THREAD; ++k) {
@@ -630,8 +709,8 @@ k_zb_collect(const RasterArgs a) {
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const long long sidx = cta0 + k * ZB_THREADS + (tid & ~31) + src;
-            const int sb = (int)(sidx / a.nf), sf = (int)(sidx % a.nf);
+            int sb, sf;
+            view_face(k * ZB_THREADS + (tid & ~31) + src, sb, sf);
             ZbFace G;
             int gx0, gx1, gy0, gy1;
             if (!zb_setup(a, sb, sf, G, gx0, gx1, gy0, gy1)) continue;
