@@ -202,6 +202,7 @@ __device__ __forceinline__ void accumulate(float *dst_f, long long *dst_i, Index
 template <int CT, bool NEED_UV, bool DET, bool AUX>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_backward(const BackwardArgs a) {
+    pdl_wait();         // the forward's maps, tile list and zero-filled accumulators (nr_kernels.h)
     const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
     const int R = a.R, S = a.S, C = CT ? CT : a.C;
     const int nt = a.ntx * a.ntx;
@@ -490,24 +491,24 @@ cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream) {
     dim3 block(TILE_THREADS);
     ProfScope p(PROF_BACKWARD, stream);
     if (a.det_verts) {
-        if (a.grad_vt) k_backward<0, true, true, false><<<grid, block, 0, stream>>>(a);
-        else k_backward<0, false, true, false><<<grid, block, 0, stream>>>(a);
+        if (a.grad_vt) launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, true, true, false>, dim3(grid), block, 0, stream, a);
+        else launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, false, true, false>, dim3(grid), block, 0, stream, a);
     } else if (a.grad_vt) {
-        if (a.aux) k_backward<0, true, false, true><<<grid, block, 0, stream>>>(a);
-        else k_backward<0, true, false, false><<<grid, block, 0, stream>>>(a);
+        if (a.aux) launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, true, false, true>, dim3(grid), block, 0, stream, a);
+        else launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, true, false, false>, dim3(grid), block, 0, stream, a);
     } else if (a.aux) {
         switch (a.lights.num > 0 ? 0 : a.C) {
-            case 1: k_backward<1, false, false, true><<<grid, block, 0, stream>>>(a); break;
-            case 3: k_backward<3, false, false, true><<<grid, block, 0, stream>>>(a); break;
-            case 4: k_backward<4, false, false, true><<<grid, block, 0, stream>>>(a); break;
-            default: k_backward<0, false, false, true><<<grid, block, 0, stream>>>(a); break;
+            case 1: launch_after(2, (long long)a.B * a.R * a.R, k_backward<1, false, false, true>, dim3(grid), block, 0, stream, a); break;
+            case 3: launch_after(2, (long long)a.B * a.R * a.R, k_backward<3, false, false, true>, dim3(grid), block, 0, stream, a); break;
+            case 4: launch_after(2, (long long)a.B * a.R * a.R, k_backward<4, false, false, true>, dim3(grid), block, 0, stream, a); break;
+            default: launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, false, false, true>, dim3(grid), block, 0, stream, a); break;
         }
     } else {
         switch (a.lights.num > 0 ? 0 : a.C) {
-            case 1: k_backward<1, false, false, false><<<grid, block, 0, stream>>>(a); break;
-            case 3: k_backward<3, false, false, false><<<grid, block, 0, stream>>>(a); break;
-            case 4: k_backward<4, false, false, false><<<grid, block, 0, stream>>>(a); break;
-            default: k_backward<0, false, false, false><<<grid, block, 0, stream>>>(a); break;
+            case 1: launch_after(2, (long long)a.B * a.R * a.R, k_backward<1, false, false, false>, dim3(grid), block, 0, stream, a); break;
+            case 3: launch_after(2, (long long)a.B * a.R * a.R, k_backward<3, false, false, false>, dim3(grid), block, 0, stream, a); break;
+            case 4: launch_after(2, (long long)a.B * a.R * a.R, k_backward<4, false, false, false>, dim3(grid), block, 0, stream, a); break;
+            default: launch_after(2, (long long)a.B * a.R * a.R, k_backward<0, false, false, false>, dim3(grid), block, 0, stream, a); break;
         }
     }
     cudaError_t e = cudaGetLastError();

@@ -201,6 +201,7 @@ k_bin_view(const float *__restrict__ verts, const int32_t *__restrict__ faces, i
            int32_t *__restrict__ pairs, long long pair_capacity, BinHeader *__restrict__ hdr,
            int32_t *__restrict__ tile_list) {
     namespace cg = cooperative_groups;
+    pdl_trigger();      // the raster kernel may be scheduled as this kernel's CTAs leave (it waits for all of them)
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     extern __shared__ int s_dyn[];
@@ -408,6 +409,7 @@ constexpr int WARP_SORT_SMEM = 1024;                  // ... up to this length: 
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 k_sort_tiles(const int32_t *__restrict__ tile_list, int cap, int32_t *__restrict__ pairs,
              const BinHeader *__restrict__ hdr) {
+    pdl_trigger();      // (nr_kernels.h) the raster kernel behind this one
     __shared__ int s_ids[SMEM_SORT_CAP];
     __shared__ int s_long[SORT_WARPS * 32];
     __shared__ int s_nlong;

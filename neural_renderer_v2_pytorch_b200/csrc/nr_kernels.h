@@ -73,7 +73,6 @@ struct RasterArgs {
     int *zb_head, *zb_pix_of;       // [zb_slot_cap] candidate list head / pixel of every contested pixel
     int4 *zb_nodes;                 // [zb_node_cap] (face, depth, min corner depth, next)
     int zb_slot_cap, zb_node_cap;
-    int zb_row_cost;                // work split of k_zb_faces (set by its launcher)
     // buffers the raster kernel zero-fills on the side (16-byte aligned, bytes a multiple of 4)
     int num_zero;
     void *zero_ptr[4];
@@ -105,6 +104,33 @@ struct BackwardArgs {
     float eps;
 };
 cudaError_t launch_backward(const BackwardArgs &a, cudaStream_t stream);
+
+// ---- programmatic dependent launch: a kernel launched with launch_after() may start (block scheduling, its
+// prologue) while the kernel in front of it on the stream is still draining; it must call pdl_wait() before it
+// touches anything that kernel (or an earlier one) wrote, and the kernel in front lets it go with pdl_trigger().
+// Both are no-ops in a kernel launched the ordinary way.  It pays where a chain of short kernels is bound by
+// launch latency (config 3: -6 %) and costs about 1 % where the kernels fill the machine for long (configs 2 and 4):
+// the launchers ask for it for calls of up to PDL_MAX_PIXELS pixels.  NR_PDL=<mask> overrides (0 = never).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+constexpr long long PDL_MAX_PIXELS = 4ll << 20;
+bool pdl_enabled(int which, long long pixels);    // which: 1 raster kernel, 2 backward kernel, 4 passes of the z-buffer path
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_after(int which, long long pixels, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(which, pixels) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 cudaError_t launch_differentiation_backward(const float *images, const float *grad_output,
                                             float *grad_coordinates, int B, int R, int C,

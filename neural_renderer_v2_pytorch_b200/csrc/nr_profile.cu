@@ -1,3 +1,4 @@
+#include <cstdlib>
 // nr_profile.cu -- optional per-kernel CUDA-event timing (nr_profile_enable / nr_profile_collect).
 #include <atomic>
 #include <mutex>
@@ -67,3 +68,15 @@ int nr_profile_collect(float *ms, int32_t *launches) {
 }
 
 }  // extern "C"
+
+namespace nr {
+bool pdl_enabled(int which, long long pixels) {
+    static int mask = -2;
+    if (mask == -2) {
+        const char *e = getenv("NR_PDL");
+        mask = e ? atoi(e) : -1;
+    }
+    if (mask >= 0) return (mask & which) != 0;      // forced
+    return pixels <= PDL_MAX_PIXELS;
+}
+}  // namespace nr

@@ -92,6 +92,8 @@ __device__ __noinline__ float exact_zp_call(float w0, float w1, float w2, float 
 template <bool RGB, bool AA, bool FULL, bool FINE>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_raster(const RasterArgs a) {
+    pdl_wait();         // the binning kernel's records, lists and header (nr_kernels.h)
+    pdl_trigger();      // the backward may be scheduled as this kernel's CTAs leave
     // a tile is 16x16 pixels = 8 warp blocks (8x4 each), or in the FINE variants 8x8 = 2 blocks
     constexpr int TSZ = FINE ? FINE_TILE : TILE, BLK_SHIFT = FINE ? 1 : 3, BLKS = 1 << BLK_SHIFT;
     __shared__ float4 s_rec[RASTER_WARPS][32][REC_Q];
@@ -378,23 +380,23 @@ cudaError_t launch_raster(const RasterArgs &a, cudaStream_t stream) {
     ProfScope p(PROF_RASTER, stream);
     if (a.fine) {       // dense meshes: the full-featured kernels over 8x8 tiles
         switch ((rgb ? 1 : 0) | (aa ? 2 : 0)) {
-            case 0: k_raster<false, false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-            case 1: k_raster<true, false, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-            case 2: k_raster<false, true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-            default: k_raster<true, true, true, true><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+            case 0: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, false, true, true>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+            case 1: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, false, true, true>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+            case 2: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, true, true, true>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+            default: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, true, true, true>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
         }
         return cudaGetLastError();
     }
     const int variant = (rgb ? 1 : 0) | (aa ? 2 : 0) | (full ? 4 : 0);
     switch (variant) {
-        case 0: k_raster<false, false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 1: k_raster<true, false, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 2: k_raster<false, true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 3: k_raster<true, true, false, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 4: k_raster<false, false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 5: k_raster<true, false, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        case 6: k_raster<false, true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
-        default: k_raster<true, true, true, false><<<grid, TILE_THREADS, 0, stream>>>(a); break;
+        case 0: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, false, false, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 1: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, false, false, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 2: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, true, false, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 3: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, true, false, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 4: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, false, true, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 5: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, false, true, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        case 6: launch_after(1, (long long)a.B * a.R * a.R, k_raster<false, true, true, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
+        default: launch_after(1, (long long)a.B * a.R * a.R, k_raster<true, true, true, false>, dim3(grid), dim3(TILE_THREADS), 0, stream, a); break;
     }
     return cudaGetLastError();
 }

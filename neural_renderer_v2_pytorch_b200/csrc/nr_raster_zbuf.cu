@@ -33,7 +33,6 @@
 // If the candidate pool overflows (nrBinStats.overflow; the host grows it for the next call) the lists are
 // unusable and every contested pixel is decided by the reference's own loop over ALL faces of its view, one warp
 // per pixel: slow, exact.
-#include <cstdlib>
 #include "nr_shade.cuh"
 
 namespace nr {
@@ -158,7 +157,7 @@ struct ZbFacesShared {
     int pixbase[ZB_THREADS];        // index of pixel (xlo, ylo) of the face's view in the z-buffer
     int fid[ZB_THREADS];            // face | ZB_F_* << 29  (huge faces: the plain face index, see `view`)
     int view[ZB_THREADS];           // huge faces only
-    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the box costs (rows x (width + a.zb_row_cost)) in width order (huge faces count 0)
+    int pre[ZB_THREADS + 1];        // exclusive prefix sum of the box costs (rows x (width + ZB_ROW_COST)) in width order (huge faces count 0)
     int start[ZB_THREADS + 1];      // first box pixel of every thread (a row boundary)
     int hist[40];                   // faces per width (0..31 = width - 1, 32 = huge), then their first positions
     int wsum[ZB_THREADS / 32];
@@ -242,12 +241,6 @@ __device__ __forceinline__ void zb_drain(const RasterArgs &a, const ZbFacesShare
             if (flags & (1u << k)) zb_flag_pix(a, pix[k]);
         flags = 0u;
     }
-    if (a.flags & (1 << 28)) {        // experiment: no atomics
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (go[k] && zf[k] == 12345.678f) zb_flag_pix(a, pix[k] + fv[k]);
-        return;
-    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (go[k]) old[k] = atomicMin(a.zbuf + pix[k], zb_key(zf[k], fv[k]));
@@ -269,6 +262,7 @@ __device__ __forceinline__ void zb_drain(const RasterArgs &a, const ZbFacesShare
 template <bool POW2>
 __global__ void __launch_bounds__(ZB_THREADS, 4)
 k_zb_faces(const RasterArgs a) {
+    pdl_trigger();      // (nr_kernels.h) the next pass may be scheduled as this one's CTAs leave
     __shared__ ZbFacesShared sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int R = a.R;
@@ -340,7 +334,7 @@ k_zb_faces(const RasterArgs a) {
     // ---- the boxes end to end, in width order
     {
         const int wh_ = tid < n_rows ? sh.wh[tid] : 0;
-        const int my = tid < n_rows ? ((wh_ & 0xffff) + a.zb_row_cost) * (int)((unsigned)wh_ >> 16) : 0;
+        const int my = tid < n_rows ? ((wh_ & 0xffff) + ZB_ROW_COST) * (int)((unsigned)wh_ >> 16) : 0;
         int inc = my;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -371,20 +365,19 @@ k_zb_faces(const RasterArgs a) {
                 if (sh.pre[mid] > t0) hi = mid; else lo = mid + 1;
             }
             p = lo - 1;
-            const int wh_ = sh.wh[p], fw_ = (wh_ & 0xffff) + a.zb_row_cost;
+            const int wh_ = sh.wh[p], fw_ = (wh_ & 0xffff) + ZB_ROW_COST;
             row = (t0 - sh.pre[p] + fw_ - 1) / fw_;
             if (row == (int)((unsigned)wh_ >> 16)) {
                 ++p;
                 row = 0;
             }
-            st = sh.pre[p] + row * (p < n_rows ? (sh.wh[p] & 0xffff) + a.zb_row_cost : 0);
+            st = sh.pre[p] + row * (p < n_rows ? (sh.wh[p] & 0xffff) + ZB_ROW_COST : 0);
         }
         sh.start[tid] = st;
         if (tid == 0) sh.start[ZB_THREADS] = total;
         __syncthreads();
     }
     int rem = sh.start[tid + 1] - sh.start[tid];          // cost of this thread's rows
-    if (a.flags & (1 << 29)) return;  // experiment: setup only
     // The warps run on their own from here.
     unsigned *ring = sh.ring[wid];
     const float step = 2.f * grid.invR;              // POW2: centre(i + 1) = centre(i) + 2 / R, exactly
@@ -434,7 +427,6 @@ k_zb_faces(const RasterArgs a) {
                 mask &= mask - 1;
             }
             tail += __shfl_sync(0xffffffffu, inc, 31);
-            if (a.flags & (1 << 30)) head = tail;     // experiment: no drain
             while (tail - head >= ZB_DRAIN) {
                 __syncwarp();
                 zb_drain<POW2>(a, sh, ring, head, ZB_DRAIN, lane, grid);
@@ -444,7 +436,7 @@ k_zb_faces(const RasterArgs a) {
         }
         // ---- next row
         if (act) {
-            rem -= fw + a.zb_row_cost;
+            rem -= fw + ZB_ROW_COST;
             if (++row == fh) {
                 row = 0;
                 ++p;
@@ -503,6 +495,8 @@ k_zb_faces(const RasterArgs a) {
 // shade pass) the way from the pixel to the slot.
 __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_slots(const RasterArgs a, long long words) {
+    pdl_wait();
+    pdl_trigger();
     const long long idx = (long long)blockIdx.x * ZB_THREADS + threadIdx.x;
     if (idx == 0) {
 #pragma unroll
@@ -588,6 +582,8 @@ k_zb_collect(const RasterArgs a) {
     __shared__ uint2 s_qbox[ZB_COLLECT_FACES];
     __shared__ int2 s_pairs[ZB_PAIR_CAP];
     __shared__ int s_n, s_np;
+    pdl_wait();
+    pdl_trigger();
     if (a.hdr->zb_slots == 0) return;                     // nothing contested (uniform over the grid)
     const int tid = threadIdx.x, lane = tid & 31;
     const long long total = (long long)a.B * a.nf;
@@ -798,6 +794,8 @@ struct ZbResolveShared {
 
 __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_resolve(const RasterArgs a, long long words) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ ZbResolveShared sh;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const PixGrid grid(a.R);
@@ -877,6 +875,8 @@ k_zb_resolve(const RasterArgs a, long long words) {
 template <bool RGB, bool AA, bool FULL>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_zb_shade(const RasterArgs a) {
+    pdl_wait();
+    pdl_trigger();      // the backward
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int R = a.R;
     const PixGrid grid(R);
@@ -920,16 +920,7 @@ k_zb_shade(const RasterArgs a) {
     }
 }
 
-cudaError_t launch_raster_zbuf(const RasterArgs &a_in, cudaStream_t stream) {
-    RasterArgs a = a_in;
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char *e = getenv("NR_ZB_DEBUG"); dbg = e ? atoi(e) : 0; }
-        a.flags |= (dbg & 7) << 28;
-        static int rc = -1;
-        if (rc < 0) { const char *e = getenv("NR_ZB_ROW_COST"); rc = e ? atoi(e) : ZB_ROW_COST; }
-        a.zb_row_cost = rc;
-    }
+cudaError_t launch_raster_zbuf(const RasterArgs &a, cudaStream_t stream) {
     if (a.B <= 0 || a.R <= 0) return cudaSuccess;
     const long long faces = (long long)a.B * a.nf, words = (long long)a.B * a.R * a.zb_wpr;
     const long long plane = (long long)a.B * a.R * a.R;
@@ -949,21 +940,21 @@ cudaError_t launch_raster_zbuf(const RasterArgs &a_in, cudaStream_t stream) {
     }
     {
         ProfScope p(PROF_ZB_RESOLVE, stream);
-        k_zb_slots<<<(unsigned)((words + ZB_THREADS - 1) / ZB_THREADS), ZB_THREADS, 0, stream>>>(a, words);
+        launch_after(4, (long long)a.B * a.R * a.R, k_zb_slots, dim3((unsigned)((words + ZB_THREADS - 1) / ZB_THREADS)), dim3(ZB_THREADS), 0, stream, a, words);
         if (face_ctas)
-            k_zb_collect<<<(unsigned)((faces + ZB_THREADS * ZB_COLLECT_PER_THREAD - 1) / (ZB_THREADS * ZB_COLLECT_PER_THREAD)), ZB_THREADS, 0, stream>>>(a);
-        k_zb_resolve<<<a.sm_count * 4, ZB_THREADS, 0, stream>>>(a, words);
+            launch_after(4, (long long)a.B * a.R * a.R, k_zb_collect, dim3((unsigned)((faces + ZB_COLLECT_FACES - 1) / ZB_COLLECT_FACES)), dim3(ZB_THREADS), 0, stream, a);
+        launch_after(4, (long long)a.B * a.R * a.R, k_zb_resolve, dim3(a.sm_count * 4), dim3(ZB_THREADS), 0, stream, a, words);
     }
     const bool rgb = (a.flags & FLAG_RGB) != 0, aa = (a.flags & FLAG_AA) != 0;
     const bool full = a.lights.num > 0 || a.lights.backgrounds || a.wmap || a.dmap || !a.images || (a.R & 15);
     const unsigned tiles = (unsigned)((long long)a.B * a.ntx * a.ntx);
     ProfScope p(PROF_ZB_SHADE, stream);
     // silhouettes of dense meshes are the measured case; everything else takes the full-featured variants
-    if (!rgb && !aa && !full) k_zb_shade<false, false, false><<<tiles, TILE_THREADS, 0, stream>>>(a);
-    else if (rgb && aa) k_zb_shade<true, true, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
-    else if (rgb) k_zb_shade<true, false, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
-    else if (aa) k_zb_shade<false, true, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
-    else k_zb_shade<false, false, true><<<tiles, TILE_THREADS, 0, stream>>>(a);
+    if (!rgb && !aa && !full) launch_after(4, (long long)a.B * a.R * a.R, k_zb_shade<false, false, false>, dim3(tiles), dim3(TILE_THREADS), 0, stream, a);
+    else if (rgb && aa) launch_after(4, (long long)a.B * a.R * a.R, k_zb_shade<true, true, true>, dim3(tiles), dim3(TILE_THREADS), 0, stream, a);
+    else if (rgb) launch_after(4, (long long)a.B * a.R * a.R, k_zb_shade<true, false, true>, dim3(tiles), dim3(TILE_THREADS), 0, stream, a);
+    else if (aa) launch_after(4, (long long)a.B * a.R * a.R, k_zb_shade<false, true, true>, dim3(tiles), dim3(TILE_THREADS), 0, stream, a);
+    else launch_after(4, (long long)a.B * a.R * a.R, k_zb_shade<false, false, true>, dim3(tiles), dim3(TILE_THREADS), 0, stream, a);
     return cudaGetLastError();
 }
 
