@@ -637,7 +637,7 @@ def run_ours(args):
         "collective": (None if not shared or world == 1 else
                        ("none (study: gradient left un-reduced)" if args.no_collective else
                         ("fused into the camera backward kernel over NVLink peer memory"
-                         if nr.parallel.FUSED_ALLREDUCE and nr.parallel._Exchange.get(inp["nv"], None, dev) is not None
+                         if nr.parallel.fused_allowed(world) and nr.parallel._Exchange.get(inp["nv"], None, dev) is not None
                          else "ncclAllReduce"))),
         "host_ms_per_step": round(host_ms, 4),
         "clocks": clocks,

@@ -100,9 +100,17 @@ class _Exchange:
         return cls._cache[key]
 
 
-# The fused exchange is a collective every rank must enter the same number of times; set to False (or
-# NR_FUSED_ALLREDUCE=0) to keep the NCCL all-reduce.
-FUSED_ALLREDUCE = __import__("os").environ.get("NR_FUSED_ALLREDUCE", "1") == "1"
+# The fused exchange is a collective every rank must enter the same number of times.  Measured on one 8-GPU
+# B200 box (config 3, profiles/r2_scaling_cfg3.jsonl): 2.4 % / 1.5 % faster than ncclAllReduce inside the captured
+# step on 2 / 4 GPUs, 3 % slower on 8 (every CTA waits for seven peers and reads seven slices): it is the default
+# up to FUSED_MAX_WORLD ranks.  NR_FUSED_ALLREDUCE=1 forces it for any world size, =0 keeps the NCCL all-reduce.
+_FUSED_ENV = __import__("os").environ.get("NR_FUSED_ALLREDUCE")
+FUSED_ALLREDUCE = _FUSED_ENV != "0"
+FUSED_MAX_WORLD = 4
+
+
+def fused_allowed(world_size):
+    return FUSED_ALLREDUCE and (_FUSED_ENV == "1" or world_size <= FUSED_MAX_WORLD)
 
 
 class _ShareAcrossRanks(torch.autograd.Function):
@@ -132,9 +140,9 @@ def share_across_ranks(param, group=None):
     even see a separate all-reduce: its camera-backward kernel exchanges the gradient slices with the peer GPUs
     over NVLink itself (``_Exchange``), in rank order, so the result is bit-identical on every rank."""
     out = _ShareAcrossRanks.apply(param, group)
-    if (FUSED_ALLREDUCE and param.is_cuda and param.ndim == 3 and param.shape[0] == 1 and param.shape[2] == 3
+    if (param.is_cuda and param.ndim == 3 and param.shape[0] == 1 and param.shape[2] == 3
             and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-            and dist.get_backend(group) == "nccl"):
+            and fused_allowed(dist.get_world_size(group)) and dist.get_backend(group) == "nccl"):
         # camera.transform_vertices takes `param` itself as its autograd input when it fuses the exchange, so
         # this node only reduces what OTHER consumers of `out` send back
         out._nr_shared = (param, group)
