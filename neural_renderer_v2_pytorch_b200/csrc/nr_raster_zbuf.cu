@@ -497,17 +497,42 @@ __global__ void __launch_bounds__(ZB_THREADS)
 k_zb_slots(const RasterArgs a, long long words) {
     pdl_wait();
     pdl_trigger();
+    __shared__ int s_warp[ZB_THREADS / 32], s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long idx = (long long)blockIdx.x * ZB_THREADS + threadIdx.x;
     if (idx == 0) {
 #pragma unroll
         for (int k = 0; k < TILE_LIST_HDR; ++k) const_cast<int32_t *>(a.tile_list)[k] = 0;
     }
-    if (idx >= words) return;
-    unsigned w = a.zb_bitmap[idx];
-    if (!w) return;
+    unsigned w = idx < words ? a.zb_bitmap[idx] : 0u;
+    if (!__syncthreads_or(w != 0u)) return;               // (most CTAs of most calls)
+    // the CTA takes its slots with ONE atomic (tens of thousands of them on one address would queue up in L2)
     const int n = __popc(w);
-    int slot = atomicAdd(&a.hdr->zb_slots, n);
-    atomicAdd(&a.hdr->total_pairs, n);                    // reported to the host: contested pixels of this call
+    int inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < ZB_THREADS / 32; ++k) {
+            const int c = s_warp[k];
+            s_warp[k] = tot;
+            tot += c;
+        }
+        s_base = 0;
+        if (tot) {
+            s_base = atomicAdd(&a.hdr->zb_slots, tot);
+            atomicAdd(&a.hdr->total_pairs, tot);          // reported to the host: contested pixels of this call
+        }
+    }
+    __syncthreads();
+    if (!w) return;
+    int slot = s_base + s_warp[wid] + inc - n;
     const long long row = idx / a.zb_wpr;                 // = b * R + y
     const int xw = (int)(idx % a.zb_wpr) * 32;
     {

@@ -97,3 +97,35 @@ def test_dense_random_1024(refmod, nr):
     fim_d, wm_d = ours_dense(nr, faces, 1024, 0.1, 100.0, 1)
     assert np.array_equal(fim_d, fim_ref), "dense raster kernel: %d px differ" % (fim_d != fim_ref).sum()
     assert np.array_equal(wm_d, wm_ref)
+
+
+def _stacked_faces(n, S, seed, jitter, box=0.08, views=1):
+    """n triangles that all cover the same few dozen pixels at depths within `jitter` of each other: every pixel
+    under them is a near-tie, i.e. the order-dependent z-test (rasterize_cuda_kernel.cu:145-148) decides."""
+    rng = np.random.RandomState(seed)
+    c = rng.uniform(-0.5, 0.5, size=(views, 1, 1, 2)).astype(np.float32)
+    xy = (c + rng.uniform(-box, box, size=(views, n, 3, 2))).astype(np.float32)
+    z = (1.5 + rng.uniform(-jitter, jitter, size=(views, n, 3, 1))).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([xy, z], -1))
+
+
+@pytest.mark.parametrize("n,jitter", [(300, 2e-4), (5000, 3e-4), (5000, 5e-2)])
+def test_dense_path_with_piles_of_near_ties(refmod, nr, n, jitter):
+    """The z-buffer rasterizer on its worst case: thousands of faces over the same pixels with depths inside
+    (and around) the 1e-4 hysteresis.  Every covered pixel is contested, a CTA's (face, contested pixel) pairs
+    outgrow their shared-memory queue, pixels hold more candidates than the resolve pass sorts (it then replays
+    the reference's loop over all faces), and with the default pool the candidate nodes overflow on the first
+    call.  The map must still be the reference kernel's, bit for bit."""
+    S = 128
+    faces = _stacked_faces(n, S, 1234 + n, jitter)
+    fim_ref, wm_ref = mk.run_reference(refmod, faces, S, 0.1, 100.0, 1)
+    assert (fim_ref >= 0).sum() > 50
+    fim_c = oracle.face_index_map(faces, S)
+    assert np.array_equal(fim_c, fim_ref), "C oracle != reference kernel"
+    fim_o, wm_o = ours(nr, faces, S, 0.1, 100.0, 1)
+    assert np.array_equal(fim_o, fim_ref), "tile pipeline: %d px differ" % (fim_o != fim_ref).sum()
+    for attempt in range(3):        # the host grows the candidate pool from the statistics of earlier calls
+        fim_d, wm_d = ours_dense(nr, faces, S, 0.1, 100.0, 1)
+        assert np.array_equal(fim_d, fim_ref), "z-buffer path, call %d: %d px differ" % (attempt, (fim_d != fim_ref).sum())
+        assert np.array_equal(wm_d, wm_ref)
+        torch.cuda.synchronize()
