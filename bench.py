@@ -179,6 +179,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = False                 # samples count only while the timed region runs
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -192,13 +193,18 @@ class ClockSampler(threading.Thread):
             self.ok = False
 
     def sample(self):
+        """One NVML query; it is kept only while a timed region runs (the queries before it warm NVML up: the
+        first ones take tens of milliseconds)."""
         if not self.ok:
             return
         nv = self.nv
         try:
-            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
                 nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            if not self.active:
+                return
+            self.samples.append(mhz)
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                      0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
             for bit, name in names.items():
@@ -210,7 +216,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self._stop_evt.is_set():
             self.sample()
-            self._stop_evt.wait(0.002)
+            self._stop_evt.wait(0.004)
 
     def stop(self):
         self._stop_evt.set()
@@ -384,27 +390,45 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):      # warm replays: clocks ramp up, lazy kernel loading is over
         run_step()
     # ... and a dress rehearsal of the timed loop (untimed): on a fresh box the first few hundred replays can be
-    # paced by the host (lazy initialisation in the driver), which is not what the metric is about
-    # (a fixed count: with a shared mesh every replay holds a collective, so the ranks must agree on it)
-    for _ in range(2):
-        for _ in range(args.steps):
-            run_step()
-        torch.cuda.synchronize(dev)
-    barrier()
+    # paced by the host (lazy initialisation in the driver), which is not what the metric is about.  At least
+    # twice the timed loop and at least ~0.4 s of replays (short steps need hundreds of them); the count is agreed
+    # between the ranks, because with a shared mesh every replay holds a collective.
+    # (the NVML sampler thread is set up here, not between the rehearsal and the timed region: its start-up takes
+    # milliseconds during which the GPU would idle)
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     if sampler:
         sampler.start()
+    t_reh = time.perf_counter()
+    for _ in range(args.steps):
+        run_step()
+    torch.cuda.synchronize(dev)
+    t_reh = max(time.perf_counter() - t_reh, 1e-6)
+    more = max(args.steps, int(0.4 / t_reh * args.steps))
+    if world > 1:
+        tm = torch.tensor([more], device=dev, dtype=torch.int64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        more = int(tm.item())
+    more = min(more, 20000)
+    for _ in range(more):
+        run_step()
+    torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.active = True
     e0.record()
     t_host0 = time.perf_counter()
     for i in range(args.steps):
         run_step()
-        if sampler and i == args.steps // 2:
-            sampler.sample()
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     e1.record()
+    # (no NVML call from this thread while it still has launches to issue: one query can take milliseconds, and a
+    # short step would run dry behind it.  Here everything is enqueued and the GPU is still working through it)
+    if sampler:
+        sampler.sample()
     barrier()
+    if sampler:
+        sampler.active = False
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -541,10 +565,14 @@ def run_ours(args):
 
     def timed(fn_, n):
         barrier()
+        if sampler:
+            sampler.active = True
         e0.record()
         fn_(n)
         e1.record()
         barrier()
+        if sampler:
+            sampler.active = False
         t_ = e0.elapsed_time(e1)
         if world > 1:
             tt = torch.tensor([t_], device=dev)
