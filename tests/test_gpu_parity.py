@@ -169,6 +169,46 @@ def test_renderer_end_to_end(nr):
     assert np.abs(gv - gw).max() <= 2e-2 * np.abs(gw).max()
 
 
+def test_renderer_end_to_end_tight(nr):
+    """The same Renderer.render step with the cross-device rounding of the camera transform taken out: the oracle
+    rasterizes the screen-space vertices the GPU's fused camera kernel produced, so images and the gradient that
+    reaches the camera transform must agree at the usual bars (test_renderer_end_to_end has to allow flipped
+    pixels); the camera kernels themselves are compared with torch in test_fused_camera_*."""
+    from oracle import pipeline as ref
+    d = np.load(os.path.join(GOLDEN, "renderer_rgba_aa_32.npz"))
+    dev = "cuda:0"
+    r = nr.Renderer()
+    r.image_size = int(d["image_size"])
+    r.viewpoints = torch.from_numpy(d["viewpoints"]).to(dev)
+    faces = torch.from_numpy(d["faces"]).to(dev)
+    vt, ft = torch.from_numpy(d["vertices_textures"]), torch.from_numpy(d["faces_textures"])
+    G = torch.from_numpy(d["grad_images"])
+    with torch.no_grad():
+        screen = r.transform_vertices(torch.from_numpy(d["vertices_world"]).to(dev)).contiguous()
+    # ours: rasterize_rgba on those vertices, as Renderer.render does behind the transform
+    v1 = screen.clone().requires_grad_(True)
+    t1 = torch.from_numpy(d["textures"]).to(dev).requires_grad_(True)
+    img1 = nr.rasterize_rgba(v1, faces, nr.RasterizeParam(vertices_textures=vt.to(dev), faces_textures=ft.to(dev), textures=t1),
+                             r._hyperparams())
+    (img1 * G.to(dev)).sum().backward()
+    # oracle: the reference's algorithm on the SAME screen-space vertices
+    v0 = screen.cpu().clone().requires_grad_(True)
+    t0 = torch.from_numpy(d["textures"]).clone().requires_grad_(True)
+    img0 = ref.rasterize(v0, d["faces"], r.image_size, r.anti_aliasing, near=r.near, far=r.far, draw_backside=r.draw_backside,
+                         draw_rgb=True, draw_silhouettes=True, vertices_textures=vt, faces_textures=ft.numpy(), textures=t0)
+    (img0 * G).sum().backward()
+    np.testing.assert_allclose(img1.detach().cpu().numpy(), img0.detach().numpy(), rtol=1e-5, atol=1e-6)
+    grad_close(v1.grad.cpu().numpy(), v0.grad.numpy(), "grad_vertices (screen space)")
+    grad_close(t1.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures")
+    # ... and the whole Renderer.render agrees with the two halves put together
+    vw = torch.from_numpy(d["vertices_world"]).to(dev).requires_grad_(True)
+    t2 = torch.from_numpy(d["textures"]).to(dev).requires_grad_(True)
+    img2 = r.render(vw, faces, vt.to(dev), ft.to(dev), t2)
+    (img2 * G.to(dev)).sum().backward()
+    assert torch.equal(img2, img1)
+    grad_close(t2.grad.cpu().numpy(), t0.grad.numpy(), "grad_textures through Renderer.render")
+
+
 def test_reference_golden_png(nr):
     """The one golden IMAGE the reference ships for this path: tests_torch/data/4e4987...png, which
     tests_torch/test_save_obj.py:13-43 and tests_chainer/test_rasterize.py:43-72 compare with a render of
