@@ -1,4 +1,7 @@
-# scaling study on one 8-GPU box: strong-scaled config 2, weak-scaled config 3 (fused all-reduce and NCCL)
+#!/bin/bash
+# Scaling study on one 8-GPU box (gpurun --gpus 8 -- 'bash tools/scaling_study.sh'): strong-scaled config 2,
+# weak-scaled config 3 with the fused exchange and with NCCL, and the shared-mesh gradient check on 8 ranks.
+# The lines it appends to gpurun_out/r3u_*.jsonl are what profiles/r2_scaling_*.jsonl hold.
 run() { # n workload extra-env out
   env $3 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) bench.py --gpus $1 --workload $2 --steps 300 --warmup 10 2>> gpurun_out/r3u_multi.err | tail -1 >> $4
 }
