@@ -80,3 +80,32 @@ def test_single_process_is_a_no_op():
     y = parallel.share_across_views(p, 3)
     y.sum().backward()
     assert torch.allclose(p.grad, torch.full_like(p, 3.0))
+
+
+def test_fused_exchange_is_the_default_up_to_four_ranks(monkeypatch):
+    """parallel.fused_allowed: the NVLink exchange inside the camera backward is the default where it measured
+    faster than ncclAllReduce (2 and 4 GPUs, profiles/r2_scaling_cfg3.jsonl); NR_FUSED_ALLREDUCE forces either."""
+    from neural_renderer_v2_pytorch_b200 import parallel
+    monkeypatch.setattr(parallel, "_FUSED_ENV", None)
+    monkeypatch.setattr(parallel, "FUSED_ALLREDUCE", True)
+    assert [parallel.fused_allowed(n) for n in (2, 4, 8)] == [True, True, False]
+    monkeypatch.setattr(parallel, "_FUSED_ENV", "1")
+    assert parallel.fused_allowed(8)
+    monkeypatch.setattr(parallel, "FUSED_ALLREDUCE", False)
+    assert not parallel.fused_allowed(2)
+
+
+def test_bench_shards_config2_strongly():
+    """bench.shard_of: config 2's batch of 64 is split over the ranks (contiguous, balanced, complete); the other
+    workloads keep their batch per GPU."""
+    import bench
+    w = bench.WORKLOADS["cfg2"]
+    for world in (1, 2, 3, 4, 8):
+        got = [bench.shard_of(w, r, world, "strong") for r in range(world)]
+        assert all(g[0] == 64 for g in got)
+        assert got[0][1] == 0 and got[-1][2] == 64
+        assert all(got[i][2] == got[i + 1][1] for i in range(world - 1))
+        sizes = [hi - lo for _, lo, hi in got]
+        assert max(sizes) - min(sizes) <= 1
+    V, lo, hi = bench.shard_of(bench.WORKLOADS["cfg3"], 3, 8, "weak")
+    assert (V, lo, hi) == (64, 24, 32)
