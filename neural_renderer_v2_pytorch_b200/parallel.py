@@ -101,16 +101,16 @@ class _Exchange:
 
 
 # The fused exchange is a collective every rank must enter the same number of times.  Measured on one 8-GPU
-# B200 box (config 3, profiles/r2_scaling_cfg3.jsonl): 2.4 % / 1.5 % faster than ncclAllReduce inside the captured
-# step on 2 / 4 GPUs, 3 % slower on 8 (every CTA waits for seven peers and reads seven slices): it is the default
-# up to FUSED_MAX_WORLD ranks.  NR_FUSED_ALLREDUCE=1 forces it for any world size, =0 keeps the NCCL all-reduce.
+# B200 box (config 3, profiles/r2_scaling_cfg3.jsonl): 0.183 / 0.190 / 0.212 ms per step on 2 / 4 / 8 GPUs against
+# 0.216 ms with ncclAllReduce inside the captured step on 8, and the sum is bit-identical on every rank: it is the
+# default up to FUSED_MAX_WORLD ranks (the kernel's peer table).  NR_FUSED_ALLREDUCE=0 keeps the NCCL all-reduce.
 _FUSED_ENV = __import__("os").environ.get("NR_FUSED_ALLREDUCE")
 FUSED_ALLREDUCE = _FUSED_ENV != "0"
-FUSED_MAX_WORLD = 4
+FUSED_MAX_WORLD = 16
 
 
 def fused_allowed(world_size):
-    return FUSED_ALLREDUCE and (_FUSED_ENV == "1" or world_size <= FUSED_MAX_WORLD)
+    return FUSED_ALLREDUCE and world_size <= FUSED_MAX_WORLD
 
 
 class _ShareAcrossRanks(torch.autograd.Function):

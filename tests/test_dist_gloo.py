@@ -82,15 +82,12 @@ def test_single_process_is_a_no_op():
     assert torch.allclose(p.grad, torch.full_like(p, 3.0))
 
 
-def test_fused_exchange_is_the_default_up_to_four_ranks(monkeypatch):
-    """parallel.fused_allowed: the NVLink exchange inside the camera backward is the default where it measured
-    faster than ncclAllReduce (2 and 4 GPUs, profiles/r2_scaling_cfg3.jsonl); NR_FUSED_ALLREDUCE forces either."""
+def test_fused_exchange_default(monkeypatch):
+    """parallel.fused_allowed: the NVLink exchange inside the camera backward is the default for every world size
+    its peer table holds (profiles/r2_scaling_cfg3.jsonl); NR_FUSED_ALLREDUCE=0 keeps ncclAllReduce."""
     from neural_renderer_v2_pytorch_b200 import parallel
-    monkeypatch.setattr(parallel, "_FUSED_ENV", None)
     monkeypatch.setattr(parallel, "FUSED_ALLREDUCE", True)
-    assert [parallel.fused_allowed(n) for n in (2, 4, 8)] == [True, True, False]
-    monkeypatch.setattr(parallel, "_FUSED_ENV", "1")
-    assert parallel.fused_allowed(8)
+    assert [parallel.fused_allowed(n) for n in (2, 4, 8, 16, 32)] == [True, True, True, True, False]
     monkeypatch.setattr(parallel, "FUSED_ALLREDUCE", False)
     assert not parallel.fused_allowed(2)
 

@@ -70,7 +70,7 @@ def main():
     nr.parallel.FUSED_ALLREDUCE = False
     p1 = torch.from_numpy(d["vertices"])[None].to(dev).requires_grad_(True)
     fused_step(p1)
-    nr.parallel.FUSED_ALLREDUCE, nr.parallel._FUSED_ENV = True, "1"       # (forced: the default stops at FUSED_MAX_WORLD ranks)
+    nr.parallel.FUSED_ALLREDUCE = True
     p2 = torch.from_numpy(d["vertices"])[None].to(dev).requires_grad_(True)
     fused_step(p2)
     ex = nr.parallel._Exchange.get(p2.shape[1], None, dev)
