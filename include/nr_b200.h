@@ -287,9 +287,11 @@ NR_API int nr_camera_backward(const float *vertices, const float *rotation, cons
  * NCCL call, no second kernel.  Every rank passes the same `peer_buffers`: world pointers, entry r = rank r's
  * exchange buffer of nr_camera_exchange_bytes(nv, world) bytes as mapped into THIS process (symmetric memory /
  * CUDA IPC; zero-filled once before the first call, then owned by these calls), and its own `epoch` (four ints of
- * device memory, zero-filled once; epoch[2] becomes 1 if a peer failed to show up within a few seconds).  CTA j sums its 256 vertices over the local views, publishes the slice, waits
- * for the same slice of every peer (flags in the exchange buffers, release / acquire at system scope), adds the
- * world slices in rank order and writes grad_vertices: bit-identical on every rank and from run to run.  All ranks
+ * device memory, zero-filled once; epoch[2] becomes 1 if a peer failed to show up within a few seconds).  A thread
+ * sums its vertex over the local views, pushes the three sums into its slots of every peer's buffer as 8-byte
+ * (value, epoch) words - written atomically, so no flag and no fence is needed: NCCL's LL trade - polls its own
+ * buffer for the words of every peer, adds them in rank order and writes grad_vertices: bit-identical on every
+ * rank and from run to run.  All ranks
  * must call it the same number of times (it is a collective).  The grid must be resident as a whole
  * (nv <= 256 * SMs * resident CTAs per SM: otherwise NR_ERR_INVALID_ARGUMENT, use NCCL).
  */

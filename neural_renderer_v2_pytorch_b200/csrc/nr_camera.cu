@@ -144,36 +144,34 @@ k_camera_backward_shared(const float *__restrict__ verts, const float *__restric
 // ---- shared mesh on several GPUs: camera backward FUSED with the all-reduce of its result ------------------
 // Multi-view optimisation of one mesh on N GPUs (BASELINE config 3): every rank holds B of the views; the
 // gradient of the shared [1,nv,3] mesh is the sum over all views of all ranks.  Instead of this kernel followed
-// by an NCCL all-reduce of 12*nv bytes (25 - 40 us of latency for 0.6 MB on a step of 0.19 ms), the exchange
-// happens INSIDE the kernel over NVLink peer memory (every rank maps every rank's buffer: symmetric memory):
+// by an NCCL all-reduce of 12*nv bytes (a 0.16 ms step grows by 50 us on 8 GPUs), the exchange happens INSIDE
+// the kernel over NVLink peer memory (every rank maps every rank's buffer: symmetric memory):
 //
-//   CTA j owns 256 vertices.  It sums their gradient over the local views in registers (as above), stores the
-//   slice into this rank's exchange buffer, publishes a flag (the step's epoch) in every peer's flag array,
-//   waits for the flags of the SAME slice from every peer - nothing else: no grid barrier, no kernel boundary -
-//   then reads the N slices over NVLink, adds them IN RANK ORDER (every rank gets the same bits, run to run)
-//   and writes the result.  Slices travel while other CTAs still compute.
+//   A thread owns a vertex.  It sums the gradient over the local views in registers (as above) and PUSHES the
+//   three sums into its slots of every peer's receive buffer, each as one 8-byte word (value, epoch): the word is
+//   written atomically, so a reader that finds this step's epoch in it has the value too - no flag behind a
+//   fence (a release / acquire pair at system scope cost 20 us per step; NCCL's LL protocol makes the same
+//   trade: twice the bytes, no fence).  Then it polls its own buffer for the three words of every peer, adds
+//   them IN RANK ORDER (every rank gets the same bits, run to run) and writes the result.  Nothing else
+//   synchronises: no flags, no CTA or grid barrier, no kernel boundary; words travel while other CTAs compute.
 //
-// Buffers of two consecutive steps alternate (epoch parity): a rank can only be one step ahead of a peer it
-// exchanges flags with, so nobody overwrites a slice that is still being read.  Flags only grow (epoch numbers),
-// so they are never reset.  A CTA publishes its flag BEFORE it waits, and the grid (ceil(nv/256) CTAs) is
-// resident as a whole, so the wait cannot deadlock.
+// Receive slots of two consecutive steps alternate (epoch parity): a rank cannot be more than one step ahead of a
+// peer (it needs that peer's words of the step before), so nobody overwrites a word that is still to be read.
+// Epochs only grow, so the buffers are never reset.  A thread pushes BEFORE it polls, so the wait cannot deadlock
+// whatever part of the grid is resident.
 constexpr int CAM_MAX_RANKS = 16;
 struct PeerExchange {
     int rank, world;
-    float *data[CAM_MAX_RANKS];     // every rank's exchange buffer: [2][nv * 3] floats
-    int *flags[CAM_MAX_RANKS];      // every rank's flag array: [slices][world] epochs
-    int *epoch;                     // this rank's {step counter, CTAs done, peer timed out, -} (device memory, zeroed once)
+    unsigned long long *recv[CAM_MAX_RANKS];    // every rank's receive buffer: [2][world][nv * 3] words (value | epoch << 32)
+    int *epoch;                                  // this rank's {step counter, CTAs done, peer timed out, -} (device memory, zeroed once)
 };
 
-__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire_sys(const int *p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_word_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ float ld_peer(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_word_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -205,43 +203,38 @@ k_camera_backward_shared_exchange(const float *__restrict__ verts, const float *
         }
         if (partial) camera_block_sum(acc, s_red, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
     }
-    // ---- publish the slice
-    const size_t half = (size_t)nv * 3, off = (size_t)(e & 1) * half + 3 * (size_t)i;
     if (in) {
-        float *mine = px.data[px.rank] + off;
-        mine[0] = sum[0];
-        mine[1] = sum[1];
-        mine[2] = sum[2];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < px.world && threadIdx.x != px.rank)
-        st_release_sys(px.flags[threadIdx.x] + (size_t)blockIdx.x * px.world + px.rank, e);
-    // ---- the peers' copies of the same slice
-    if (threadIdx.x < px.world && threadIdx.x != px.rank) {
-        const int *f = px.flags[px.rank] + (size_t)blockIdx.x * px.world + threadIdx.x;
-        // (a peer that never arrives - a crashed process - must not hang the GPU: give up after a few seconds
-        // and say so in epoch[2]; the gradient of this step is then garbage)
-        long long spins = 0;
-        while (ld_acquire_sys(f) - e < 0) {
-            __nanosleep(128);
-            if (++spins > (1ll << 24)) {
-                px.epoch[2] = 1;
-                break;
-            }
+        const size_t half = (size_t)nv * 3;
+        const unsigned long long tag = (unsigned long long)(unsigned)e << 32;
+        // ---- push my words into every peer's slots [parity][my rank]
+        const size_t mine = ((size_t)(e & 1) * px.world + px.rank) * half + 3 * (size_t)i;
+        for (int r = 0; r < px.world; ++r) {
+            if (r == px.rank) continue;
+            unsigned long long *dst = px.recv[r] + mine;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st_word_sys(dst + k, tag | __float_as_uint(sum[k]));
         }
-    }
-    __syncthreads();
-    if (in) {
+        // ---- the peers' words in my buffer, added in rank order: the same sum, bit for bit, on every rank
         float t[3] = {0.f, 0.f, 0.f};
-        for (int r = 0; r < px.world; ++r) {            // rank order: the same sum, bit for bit, on every rank
+        for (int r = 0; r < px.world; ++r) {
             if (r == px.rank) {
                 t[0] += sum[0]; t[1] += sum[1]; t[2] += sum[2];
-            } else {
-                const float *p = px.data[r] + off;
-                const float a0 = ld_peer(p), a1 = ld_peer(p + 1), a2 = ld_peer(p + 2);
-                t[0] += a0; t[1] += a1; t[2] += a2;
+                continue;
             }
+            const unsigned long long *src = px.recv[px.rank] + ((size_t)(e & 1) * px.world + r) * half + 3 * (size_t)i;
+            unsigned long long w0 = ld_word_sys(src), w1 = ld_word_sys(src + 1), w2 = ld_word_sys(src + 2);
+            // (a peer that never arrives - a crashed process - must not hang the GPU: give up after a few seconds
+            // and say so in epoch[2]; the gradient of this step is then garbage)
+            long long spins = 0;
+            while ((int)(w0 >> 32) != e || (int)(w1 >> 32) != e || (int)(w2 >> 32) != e) {
+                __nanosleep(32);
+                if (++spins > (1ll << 25)) {
+                    px.epoch[2] = 1;
+                    break;
+                }
+                w0 = ld_word_sys(src); w1 = ld_word_sys(src + 1); w2 = ld_word_sys(src + 2);
+            }
+            t[0] += __uint_as_float((unsigned)w0); t[1] += __uint_as_float((unsigned)w1); t[2] += __uint_as_float((unsigned)w2);
         }
         gverts[3 * (size_t)i] = t[0];
         gverts[3 * (size_t)i + 1] = t[1];
@@ -296,10 +289,9 @@ int nr_camera_backward(const float *vertices, const float *rotation, const float
 }
 
 int nr_camera_exchange_bytes(int32_t num_vertices, int32_t world) {
-    // flags [slices][world] ints (rounded up to 256 bytes), then two buffers of nv * 3 floats
-    const size_t flags = ((size_t)nr_camera_partial_blocks(num_vertices) * world * sizeof(int) + 255) & ~(size_t)255;
-    const size_t total = flags + 2 * (size_t)num_vertices * 3 * sizeof(float);
-    return total > 0x7fffffff ? -1 : (int)total;
+    // receive slots [2 (epoch parity)][world][nv * 3] of 8-byte words
+    const size_t total = 2 * (size_t)world * (size_t)num_vertices * 3 * sizeof(unsigned long long);
+    return (num_vertices <= 0 || world < 1 || total > 0x7fffffff) ? -1 : (int)total;
 }
 
 int nr_camera_backward_shared_allreduce(const float *vertices, const float *rotation, const float *eye, const float *grad_out,
@@ -319,11 +311,9 @@ int nr_camera_backward_shared_allreduce(const float *vertices, const float *rota
     nr::PeerExchange px;
     px.rank = rank;
     px.world = world;
-    const size_t flag_bytes = ((size_t)slices * world * sizeof(int) + 255) & ~(size_t)255;
     for (int r = 0; r < world; ++r) {
         if (!peer_buffers[r]) return NR_ERR_INVALID_ARGUMENT;
-        px.flags[r] = (int *)peer_buffers[r];
-        px.data[r] = (float *)((char *)peer_buffers[r] + flag_bytes);
+        px.recv[r] = (unsigned long long *)peer_buffers[r];
     }
     px.epoch = epoch;
     nr::ProfScope p(nr::PROF_CAMERA_BACKWARD, (cudaStream_t)stream);
