@@ -101,7 +101,7 @@ class _Exchange:
 
 
 # The fused exchange is a collective every rank must enter the same number of times.  Measured on one 8-GPU
-# B200 box (config 3, profiles/r2_scaling_cfg3.jsonl): 0.183 / 0.190 / 0.212 ms per step on 2 / 4 / 8 GPUs against
+# B200 box (config 3, profiles/r2_scaling_cfg3.jsonl): 0.171 / 0.181 / 0.204 ms per step on 2 / 4 / 8 GPUs against
 # 0.216 ms with ncclAllReduce inside the captured step on 8, and the sum is bit-identical on every rank: it is the
 # default up to FUSED_MAX_WORLD ranks (the kernel's peer table).  NR_FUSED_ALLREDUCE=0 keeps the NCCL all-reduce.
 _FUSED_ENV = __import__("os").environ.get("NR_FUSED_ALLREDUCE")
