@@ -240,6 +240,9 @@ int nr_rasterize_forward(const nrRasterConfig *cfg, const float *vertices, const
     const bool dense = (cfg->flags & NR_DENSE_RASTER) != 0;
     if (dense && (long long)cfg->batch * R * R > 0x7fffffffLL)
         return fail(NR_ERR_INVALID_ARGUMENT, "NR_DENSE_RASTER: batch x pixels too large for one call: split the batch");
+    // (k_zb_faces keeps two flag bits above a face index)
+    if (dense && cfg->num_faces >= (1 << 29))
+        return fail(NR_ERR_INVALID_ARGUMENT, "NR_DENSE_RASTER: more than 2^29 faces per view");
     const Carve c = dense ? carve_dense(workspace, cfg->batch, cfg->num_faces, R, pair_capacity)
                           : carve(workspace, cfg->batch, cfg->num_faces, R, pair_capacity, tile);
     if (c.bytes > workspace_bytes) return fail(NR_ERR_WORKSPACE_TOO_SMALL, "workspace smaller than nr_workspace_bytes()");

@@ -182,7 +182,8 @@ k_camera_backward_shared_exchange(const float *__restrict__ verts, const float *
     __shared__ float s_red[CAM_THREADS / 32][12];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < nv;
-    const int e = *reinterpret_cast<volatile int *>(px.epoch) + 1;      // this step (bumped by the last CTA to finish)
+    // this step (bumped by the last CTA to finish); unsigned: it wraps after 2^32 steps, and only equality and parity are used
+    const unsigned e = (unsigned)*reinterpret_cast<volatile int *>(px.epoch) + 1u;
     float v[3] = {0.f, 0.f, 0.f}, sum[3] = {0.f, 0.f, 0.f};
     if (in) {
         v[0] = verts[3 * (size_t)i];
@@ -205,7 +206,7 @@ k_camera_backward_shared_exchange(const float *__restrict__ verts, const float *
     }
     if (in) {
         const size_t half = (size_t)nv * 3;
-        const unsigned long long tag = (unsigned long long)(unsigned)e << 32;
+        const unsigned long long tag = (unsigned long long)e << 32;
         // ---- push my words into every peer's slots [parity][my rank]
         const size_t mine = ((size_t)(e & 1) * px.world + px.rank) * half + 3 * (size_t)i;
         for (int r = 0; r < px.world; ++r) {
@@ -226,7 +227,7 @@ k_camera_backward_shared_exchange(const float *__restrict__ verts, const float *
             // (a peer that never arrives - a crashed process - must not hang the GPU: give up after a few seconds
             // and say so in epoch[2]; the gradient of this step is then garbage)
             long long spins = 0;
-            while ((int)(w0 >> 32) != e || (int)(w1 >> 32) != e || (int)(w2 >> 32) != e) {
+            while ((unsigned)(w0 >> 32) != e || (unsigned)(w1 >> 32) != e || (unsigned)(w2 >> 32) != e) {
                 __nanosleep(32);
                 if (++spins > (1ll << 25)) {
                     px.epoch[2] = 1;
@@ -247,7 +248,7 @@ k_camera_backward_shared_exchange(const float *__restrict__ verts, const float *
         if (atomicAdd(px.epoch + 1, 1) == (int)gridDim.x - 1) {
             px.epoch[1] = 0;
             __threadfence();
-            *reinterpret_cast<volatile int *>(px.epoch) = e;
+            *reinterpret_cast<volatile int *>(px.epoch) = (int)e;
         }
     }
 }
